@@ -1,0 +1,220 @@
+"""ctypes loader for the CPU oracle -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (astroz_b200) never does.
+
+The oracle is the scalar C restatement in oracle/astroz_oracle.c (parity pinned against the
+reference's golden vectors by tests/test_oracle_golden.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+
+WGS84, WGS72 = 0, 1
+OK, DECAYED, INVALID_ECC, DEEP_SPACE, OOM, BAD_TLE = 0, 1, 2, 3, 4, 5
+
+SGP4_FIELDS = [
+    "epochJd", "noKozai", "ecco", "inclo", "nodeo", "argpo", "mo", "bstar", "noUnkozai", "a",
+    "sinio", "cosio", "cosio2", "cosio4", "con41", "con42", "x1mth2", "x7thm1",
+    "mdot", "argpdot", "nodedot",
+    "cc1", "cc4", "cc5", "t2cof", "omgcof", "xnodcf", "xlcof", "xmcof", "aycof", "eta", "delmo", "sinmao",
+    "d2", "d3", "d4", "t3cof", "t4cof", "t5cof", "aBase", "vkmpersec", "isimp",
+]
+_PERT = ["e2", "e3", "i2", "i3", "l2", "l3", "l4", "gh2", "gh3", "gh4", "h2", "h3"]
+SDP4_FIELDS = (
+    ["solar_" + p for p in _PERT] + ["lunar_" + p for p in _PERT]
+    + ["zmol", "zmos", "dedt", "didt", "dmdt", "domdt", "dnodt", "irez",
+       "d2201", "d2211", "d3210", "d3222", "d4410", "d4422", "d5220", "d5232", "d5421", "d5433",
+       "del1", "del2", "del3", "xlamo", "xfact", "gsto"]
+)
+
+
+def build(force: bool = False) -> None:
+    """Compile oracle/_build/*.so with the committed Makefile (gcc only, a few seconds)."""
+    targets = [os.path.join(_BUILD, "libastroz_oracle.so"), os.path.join(_BUILD, "libastroz_simd_baseline.so")]
+    srcs = [os.path.join(_HERE, f) for f in ("astroz_oracle.c", "astroz_oracle.h", "simd_baseline.c", "Makefile")]
+    newest_src = max(os.path.getmtime(s) for s in srcs if os.path.exists(s))
+    if not force and all(os.path.exists(t) and os.path.getmtime(t) >= newest_src for t in targets):
+        return
+    subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+
+
+class _Tle(C.Structure):
+    _fields_ = [("satnum", C.c_uint32), ("epochYear", C.c_int), ("epochDay", C.c_double), ("epochJd", C.c_double),
+                ("ndot", C.c_double), ("bstar", C.c_double), ("inclDeg", C.c_double), ("raanDeg", C.c_double),
+                ("ecc", C.c_double), ("argpDeg", C.c_double), ("maDeg", C.c_double), ("nRevDay", C.c_double)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = os.path.join(_BUILD, "libastroz_oracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        dp = C.POINTER(C.c_double)
+        L.azo_tle_parse.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(_Tle)]
+        L.azo_tle_parse.restype = C.c_int
+        L.azo_year_doy_to_jd.argtypes = [C.c_int, C.c_double]
+        L.azo_year_doy_to_jd.restype = C.c_double
+        for name in ("azo_sgp4_init", "azo_sdp4_init"):
+            getattr(L, name).argtypes = [C.POINTER(_Tle), C.c_int, C.c_void_p]
+            getattr(L, name).restype = C.c_int
+        L.azo_sgp4_propagate.argtypes = [C.c_void_p, C.c_double, dp, dp]
+        L.azo_sgp4_propagate.restype = None
+        L.azo_sdp4_propagate.argtypes = [C.c_void_p, C.c_double, dp, dp]
+        L.azo_sdp4_propagate.restype = C.c_int
+        L.azo_sdp4_propagate_carry.argtypes = [C.c_void_p, C.c_double, dp, dp, dp]
+        L.azo_sdp4_propagate_carry.restype = C.c_int
+        L.azo_gstime.argtypes = [C.c_double]
+        L.azo_gstime.restype = C.c_double
+        L.azo_julian_to_gmst.argtypes = [C.c_double]
+        L.azo_julian_to_gmst.restype = C.c_double
+        L.azo_ecef_to_geodetic.argtypes = [dp, dp]
+        L.azo_sgp4_export.argtypes = [C.c_void_p, dp]
+        L.azo_sdp4_export.argtypes = [C.c_void_p, dp]
+        L.azo_constellation_propagate.argtypes = [
+            C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int, dp, dp, C.c_size_t,
+            dp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int)]
+        L.azo_constellation_propagate.restype = C.c_int
+        L.azo_satrec_array_sgp4.argtypes = [
+            C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int, dp, dp, C.c_size_t, dp, dp]
+        L.azo_satrec_array_sgp4.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _lines(tles):
+    n = len(tles)
+    a1 = (C.c_char_p * n)(*[t[0].encode() for t in tles])
+    a2 = (C.c_char_p * n)(*[t[1].encode() for t in tles])
+    return a1, a2
+
+
+def parse_tle(line1: str, line2: str) -> dict:
+    t = _Tle()
+    rc = lib().azo_tle_parse(line1.encode(), line2.encode(), C.byref(t))
+    if rc != OK:
+        raise ValueError("bad TLE")
+    return {k: getattr(t, k) for k, _ in _Tle._fields_}
+
+
+class Sgp4:
+    """Scalar SGP4 oracle for one satellite (src/Sgp4.zig:99-106)."""
+
+    def __init__(self, line1: str, line2: str, grav: int = WGS72):
+        t = _Tle()
+        if lib().azo_tle_parse(line1.encode(), line2.encode(), C.byref(t)) != OK:
+            raise ValueError("bad TLE")
+        self._buf = C.create_string_buffer(1024)
+        self.rc = lib().azo_sgp4_init(C.byref(t), grav, self._buf)
+        self.epochJd = t.epochJd
+        if self.rc == OK:
+            out = np.zeros(48)
+            lib().azo_sgp4_export(self._buf, _dp(out))
+            self.el = dict(zip(SGP4_FIELDS, out.tolist()))
+
+    def propagate(self, tsince: float):
+        r = np.zeros(3)
+        v = np.zeros(3)
+        lib().azo_sgp4_propagate(self._buf, float(tsince), _dp(r), _dp(v))
+        return r, v
+
+
+class Sdp4:
+    """Scalar SDP4 oracle for one satellite (src/Sdp4.zig:152-172)."""
+
+    def __init__(self, line1: str, line2: str, grav: int = WGS72):
+        t = _Tle()
+        if lib().azo_tle_parse(line1.encode(), line2.encode(), C.byref(t)) != OK:
+            raise ValueError("bad TLE")
+        self._buf = C.create_string_buffer(2048)
+        self.rc = lib().azo_sdp4_init(C.byref(t), grav, self._buf)
+        self.epochJd = t.epochJd
+        if self.rc == OK:
+            out = np.zeros(112)
+            lib().azo_sdp4_export(self._buf, _dp(out))
+            self.el = dict(zip(SGP4_FIELDS, out[:len(SGP4_FIELDS)].tolist()))
+            self.el.update(dict(zip(SDP4_FIELDS, out[48:48 + len(SDP4_FIELDS)].tolist())))
+        self.reset_carry()
+
+    def reset_carry(self):
+        self._carry = np.array([0.0, self.el["xlamo"], self.el["noUnkozai"]]) if self.rc == OK else np.zeros(3)
+
+    def propagate(self, tsince: float):
+        r = np.zeros(3)
+        v = np.zeros(3)
+        rc = lib().azo_sdp4_propagate(self._buf, float(tsince), _dp(r), _dp(v))
+        return rc, r, v
+
+    def propagate_carry(self, tsince: float):
+        r = np.zeros(3)
+        v = np.zeros(3)
+        rc = lib().azo_sdp4_propagate_carry(self._buf, float(tsince), _dp(self._carry), _dp(r), _dp(v))
+        return rc, r, v
+
+
+def gstime(jd: float) -> float:
+    return lib().azo_gstime(float(jd))
+
+
+def julian_to_gmst(jd: float) -> float:
+    return lib().azo_julian_to_gmst(float(jd))
+
+
+def ecef_to_geodetic(ecef) -> np.ndarray:
+    e = np.ascontiguousarray(ecef, dtype=np.float64)
+    out = np.zeros(3)
+    lib().azo_ecef_to_geodetic(_dp(e), _dp(out))
+    return out
+
+
+def constellation_propagate(tles, jd, fr, grav: int = WGS72, mode: int = 0, layout: int = 0, velocities: bool = True):
+    """Scalar oracle of Constellation.init + propagate (src/Constellation.zig:101-308).
+
+    Returns (pos, vel, err[n, nt], klass[n]); pos/vel are shaped by `layout`
+    (0: (n, nt, 3) satellite-major, 1: (nt, n, 3) time-major).
+    """
+    jd = np.ascontiguousarray(jd, dtype=np.float64)
+    fr = np.ascontiguousarray(fr, dtype=np.float64)
+    n, nt = len(tles), len(jd)
+    shape = (n, nt, 3) if layout == 0 else (nt, n, 3)
+    pos = np.zeros(shape)
+    vel = np.zeros(shape) if velocities else None
+    err = np.zeros((n, nt), dtype=np.uint8)
+    klass = np.zeros(n, dtype=np.int32)
+    a1, a2 = _lines(tles)
+    rc = lib().azo_constellation_propagate(
+        a1, a2, n, grav, _dp(jd), _dp(fr), nt, _dp(pos), _dp(vel) if velocities else None, mode, layout,
+        err.ctypes.data_as(C.POINTER(C.c_uint8)), klass.ctypes.data_as(C.POINTER(C.c_int)))
+    if rc != 0:
+        raise ValueError(f"oracle constellation init failed rc={rc}")
+    return pos, vel, err, klass
+
+
+def satrec_array_sgp4(tles, jd, fr, grav: int = WGS72):
+    """Scalar oracle of SatrecArray.sgp4 for near-earth satellites (bindings/python/astroz/api.py:249-320)."""
+    jd = np.ascontiguousarray(jd, dtype=np.float64)
+    fr = np.ascontiguousarray(fr, dtype=np.float64)
+    n, nt = len(tles), len(jd)
+    pos = np.zeros((n, nt, 3))
+    vel = np.zeros((n, nt, 3))
+    a1, a2 = _lines(tles)
+    rc = lib().azo_satrec_array_sgp4(a1, a2, n, grav, _dp(jd), _dp(fr), nt, _dp(pos), _dp(vel))
+    if rc != 0:
+        raise ValueError(f"oracle satrec_array init failed rc={rc}")
+    return pos, vel
