@@ -1,0 +1,191 @@
+"""Constellation -- host-side mirror of `astroz.Constellation` (src/Constellation.zig:76-308) over the
+CUDA C-ABI.  Same names, argument meaning and error behaviour as the reference: `init` classifies each
+TLE as SGP4 or SDP4, `propagate(jd, fr, ...)` fills (n_sats, n_times, 3) or (n_times, n_sats, 3) blocks
+in TEME / ECEF / geodetic, failed cells are zero-filled, `reset_carry` exists for drop-in use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from enum import IntEnum
+
+import numpy as np
+
+from . import _lib
+from ._lib import AstrozCudaError, as_f64, check, dptr, lib
+
+
+class OutputMode(IntEnum):  # src/Constellation.zig:30-34
+    teme = 0
+    ecef = 1
+    geodetic = 2
+
+
+class Layout(IntEnum):  # src/Constellation.zig:37-42
+    satelliteMajor = 0
+    timeMajor = 1
+
+
+def _c_lines(tles):
+    n = len(tles)
+    a1 = (C.c_char_p * n)(*[(t[0] if isinstance(t[0], bytes) else t[0].encode()) for t in tles])
+    a2 = (C.c_char_p * n)(*[(t[1] if isinstance(t[1], bytes) else t[1].encode()) for t in tles])
+    return a1, a2
+
+
+class Constellation:
+    """Mixed SGP4/SDP4 constellation resident on one B200.
+
+    Parameters
+    ----------
+    tles : sequence of (line1, line2)
+    grav : WGS72 (1, python default of the reference) or WGS84 (0)
+    device : CUDA device index
+    """
+
+    def __init__(self, tles, grav: int = _lib.WGS72, device: int = 0):
+        self._h = C.c_void_p()
+        self._free = lib().astroz_cuda_constellation_free
+        a1, a2 = _c_lines(tles)
+        check(lib().astroz_cuda_constellation_create(a1, a2, len(tles), int(grav), int(device), C.byref(self._h)))
+        n, ns, nd = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().astroz_cuda_constellation_counts(self._h, C.byref(n), C.byref(ns), C.byref(nd)))
+        self.numSatellites, self.numSgp4, self.numSdp4 = n.value, ns.value, nd.value
+        self.device = int(device)
+        self.grav = int(grav)
+
+    @classmethod
+    def init(cls, tles, grav: int = _lib.WGS72, device: int = 0) -> "Constellation":
+        """Constellation.init(allocator, tles, grav)  (src/Constellation.zig:101)."""
+        return cls(tles, grav, device)
+
+    @classmethod
+    def from_text(cls, text: str, grav: int = _lib.WGS72, device: int = 0) -> "Constellation":
+        """Build from a 2/3-line element-set blob (src/Tle.zig:103-132)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._free = lib().astroz_cuda_constellation_free
+        raw = text.encode()
+        check(lib().astroz_cuda_constellation_create_from_text(raw, len(raw), int(grav), int(device), C.byref(self._h)))
+        n, ns, nd = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().astroz_cuda_constellation_counts(self._h, C.byref(n), C.byref(ns), C.byref(nd)))
+        self.numSatellites, self.numSgp4, self.numSdp4 = n.value, ns.value, nd.value
+        self.device, self.grav = int(device), int(grav)
+        return self
+
+    def deinit(self) -> None:
+        """Constellation.deinit (src/Constellation.zig:202-210)."""
+        if getattr(self, "_h", None) is not None and self._h:
+            self._free(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = deinit
+
+    # ---- introspection ------------------------------------------------------------------------
+    @property
+    def epochs(self) -> np.ndarray:
+        out = np.empty(self.numSatellites)
+        check(lib().astroz_cuda_constellation_epochs(self._h, dptr(out)))
+        return out
+
+    @property
+    def classes(self) -> np.ndarray:
+        """0 = SGP4, 1 = SDP4 non-resonant, 2 = SDP4 synchronous, 3 = SDP4 half-day."""
+        out = np.empty(self.numSatellites, dtype=np.int32)
+        check(lib().astroz_cuda_constellation_classes(self._h, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    @property
+    def referenceEpochJd(self) -> float:
+        v = C.c_double()
+        check(lib().astroz_cuda_constellation_get_reference_epoch(self._h, C.byref(v)))
+        return v.value
+
+    @referenceEpochJd.setter
+    def referenceEpochJd(self, jd: float) -> None:
+        check(lib().astroz_cuda_constellation_set_reference_epoch(self._h, float(jd)))
+
+    def resetCarry(self) -> None:
+        """Constellation.resetCarry (src/Constellation.zig:214-218); a no-op on the device path."""
+        check(lib().astroz_cuda_constellation_reset_carry(self._h))
+
+    reset_carry = resetCarry
+
+    # ---- propagation --------------------------------------------------------------------------
+    def _shape(self, n_times: int, layout: int, rows=None):
+        rows = self.numSatellites if rows is None else rows
+        return (rows, n_times, 3) if layout == Layout.satelliteMajor else (n_times, rows, 3)
+
+    def propagate(self, jd, fr, resultsPos=None, resultsVel=None, outputMode: int = OutputMode.teme,
+                  layout: int = Layout.timeMajor, velocities: bool = True):
+        """Constellation.propagate(jd, fr, resultsPos, resultsVel, outputMode, layout)
+        (src/Constellation.zig:245-308) with host buffers.  Buffers are allocated in pinned memory when
+        not supplied.  Returns (pos, vel) shaped by `layout`; vel is None when velocities=False."""
+        jd, fr = as_f64(jd), as_f64(fr)
+        if jd.shape != fr.shape:
+            raise ValueError("jd and fr must have the same length")
+        nt = jd.shape[0]
+        shape = self._shape(nt, layout)
+        if resultsPos is None:
+            resultsPos = _lib.pinned_empty(shape)
+        if resultsVel is None and velocities:
+            resultsVel = _lib.pinned_empty(shape)
+        for buf in (resultsPos, resultsVel):
+            if buf is not None and (buf.dtype != np.float64 or not buf.flags.c_contiguous or buf.size < nt * self.numSatellites * 3):
+                # the reference reports a short buffer as SatelliteDecayed (src/Constellation.zig:255-257)
+                raise AstrozCudaError(-12, "result buffer too small or not contiguous float64")
+        check(lib().astroz_cuda_constellation_propagate(
+            self._h, dptr(jd), dptr(fr), nt, dptr(resultsPos), dptr(resultsVel) if resultsVel is not None else None,
+            int(outputMode), int(layout)))
+        return resultsPos, resultsVel
+
+    def propagate_device(self, jd, fr, pos, vel=None, status=None, outputMode: int = OutputMode.teme,
+                         layout: int = Layout.satelliteMajor, out_num_sats: int | None = None,
+                         out_sat_offset: int = 0, stream: int = 0) -> None:
+        """Same computation, results left in HBM.  pos / vel / status are torch CUDA tensors (or anything
+        with .data_ptr()) on this constellation's device; asynchronous on `stream` (a raw cudaStream_t
+        value, 0 = the handle's own stream)."""
+        jd, fr = as_f64(jd), as_f64(fr)
+        nt = jd.shape[0]
+        rows = self.numSatellites if out_num_sats is None else int(out_num_sats)
+        check(lib().astroz_cuda_constellation_propagate_device(
+            self._h, dptr(jd), dptr(fr), nt, C.c_void_p(pos.data_ptr()),
+            C.c_void_p(vel.data_ptr()) if vel is not None else None,
+            C.c_void_p(status.data_ptr()) if status is not None else None,
+            int(outputMode), int(layout), rows, int(out_sat_offset), C.c_void_p(stream) if stream else None))
+
+    def synchronize(self) -> None:
+        check(lib().astroz_cuda_constellation_synchronize(self._h))
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        check(lib().astroz_cuda_constellation_last_kernel_ms(self._h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
+
+    # ---- stateless near-earth path (Constellation.propagateConstellation, :541-605) -----------------
+    def propagate_into(self, times, positions=None, velocities=None, epoch_offsets=None,
+                       outputMode: int = OutputMode.teme, reference_jd: float = 0.0, time_major: bool = True,
+                       want_velocities: bool = True):
+        """SatrecArray.propagate_into(times, positions, velocities, epoch_offsets=...)
+        (bindings/python/src/satrec.zig:896-988): tsince = times[t] + epoch_offsets[sat] for the
+        near-earth satellites only, written time-major (n_times, n_sgp4, 3) by default."""
+        times = as_f64(times)
+        nt = times.shape[0]
+        ns = self.numSgp4
+        off = np.zeros(ns) if epoch_offsets is None else as_f64(epoch_offsets)[:ns].copy()
+        layout = Layout.timeMajor if time_major else Layout.satelliteMajor
+        shape = self._shape(nt, layout, rows=ns)
+        if positions is None:
+            positions = _lib.pinned_empty(shape)
+        if velocities is None and want_velocities:
+            velocities = _lib.pinned_empty(shape)
+        check(lib().astroz_cuda_sgp4_propagate_into(
+            self._h, dptr(times), nt, dptr(off), dptr(positions),
+            dptr(velocities) if velocities is not None else None, int(outputMode), float(reference_jd), int(layout)))
+        return positions, velocities
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    """Measured DFMA throughput of the device (the fp64 roofline denominator)."""
+    v = C.c_double()
+    check(lib().astroz_cuda_fp64_peak(int(device), C.byref(v)))
+    return v.value

@@ -1,0 +1,725 @@
+// az_capi.cu -- extern "C" boundary (include/astroz_b200.h).  Host orchestration: the device branch of
+// src/Constellation.zig (init :101-200, propagate :245-308, propagateConstellation :541-605) and the
+// single-satellite exports of src/c_api/sgp4.zig.  No CPU propagation path exists in this library:
+// without a CUDA device every propagate call returns ASTROZ_NO_DEVICE / ASTROZ_CUDA_ERROR.
+#include "../../include/astroz_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "az_kernels.cuh"
+#include "az_tables.hpp"
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int32_t cuda_fail(cudaError_t e, const char *what) {
+    g_lastError = std::string(what) + ": " + cudaGetErrorString(e);
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? ASTROZ_NO_DEVICE : ASTROZ_CUDA_ERROR;
+}
+#define AZ_CUDA(expr)                                        \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return cuda_fail(_e, #expr);  \
+    } while (0)
+
+int32_t status_to_code(int st) {  // kernel-level code -> C API code (src/c_api/sgp4.zig:22-28)
+    switch (st) {
+        case az::kOk: return ASTROZ_OK;
+        case az::kDecayed: return ASTROZ_DECAYED;
+        case az::kInvalidEcc: return ASTROZ_INVALID_ECC;
+        case az::kDeepSpace: return ASTROZ_DEEP_SPACE;
+        case az::kOom: return ASTROZ_ALLOC_FAILED;
+        case az::kBadTle: return ASTROZ_BAD_TLE_LENGTH;
+        default: return ASTROZ_UNKNOWN;
+    }
+}
+
+template <typename T>
+struct DevBuf {  // grow-only device buffer
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Constellation {
+    int device = 0;
+    az::CatalogTables cat;
+    az::GravConsts g{};
+    cudaStream_t stream = nullptr, copyStream = nullptr;
+    // element tables (resident for the life of the handle)
+    DevBuf<double> dTiles, dToff;
+    DevBuf<uint32_t> dSgp4Orig, dSdp4Orig, dIdentity;
+    DevBuf<az::Sdp4Sat> dSdp4;
+    // per-call time axis: tbase | jdFull | gsin | gcos
+    DevBuf<double> dTime;
+    double *hTime = nullptr;
+    size_t hTimeCap = 0;
+    cudaEvent_t timeCopied = nullptr;
+    bool timePending = false;
+    // stateless-path epoch offsets
+    DevBuf<double> dToffCall;
+    double *hToffCall = nullptr;
+    size_t hToffCap = 0;
+    // resonance lattice (depends on the elements only; grown when a call reaches further in time)
+    DevBuf<double2> dLattice;
+    int latticeNodes = 0;
+    // staging for the host-buffer API
+    DevBuf<double> dPos, dVel;
+    // kernel timing
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t chunkDone[64] = {};
+    bool timed = false;
+    int variant = 0;
+    int chunks = 8;
+
+    ~Constellation() {
+        cudaSetDevice(device);
+        dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release();
+        dSdp4.release(); dTime.release(); dToffCall.release(); dLattice.release(); dPos.release(); dVel.release();
+        if (hTime) cudaFreeHost(hTime);
+        if (hToffCall) cudaFreeHost(hToffCall);
+        if (timeCopied) cudaEventDestroy(timeCopied);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (auto &e : chunkDone) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+        if (copyStream) cudaStreamDestroy(copyStream);
+    }
+};
+
+int32_t upload_toff(Constellation *c) {  // src/Constellation.zig:153
+    const size_t n = c->cat.sgp4Epoch.size();
+    if (n == 0) return ASTROZ_OK;
+    std::vector<double> off(n);
+    for (size_t i = 0; i < n; ++i) off[i] = (c->cat.referenceEpochJd - c->cat.sgp4Epoch[i]) * 1440.0;
+    AZ_CUDA(c->dToff.reserve(n));
+    AZ_CUDA(cudaMemcpy(c->dToff.p, off.data(), n * 8, cudaMemcpyHostToDevice));
+    return ASTROZ_OK;
+}
+
+int32_t finish_create(Constellation *c, int device) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_lastError = "no CUDA device available (this library has no CPU propagation path)";
+        return ASTROZ_NO_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        g_lastError = "device index out of range";
+        return ASTROZ_VALUE_ERROR;
+    }
+    c->device = device;
+    AZ_CUDA(cudaSetDevice(device));
+    AZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    AZ_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    AZ_CUDA(cudaEventCreateWithFlags(&c->timeCopied, cudaEventDisableTiming));
+    for (auto &ev : c->ev) AZ_CUDA(cudaEventCreate(&ev));
+    for (auto &ev : c->chunkDone) AZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    c->g = az::grav_consts(c->cat.grav);
+    const az::CatalogTables &t = c->cat;
+    if (t.nSgp4) {
+        AZ_CUDA(c->dTiles.reserve(t.sgp4Tiles.size()));
+        AZ_CUDA(cudaMemcpy(c->dTiles.p, t.sgp4Tiles.data(), t.sgp4Tiles.size() * 8, cudaMemcpyHostToDevice));
+        AZ_CUDA(c->dSgp4Orig.reserve(t.sgp4Orig.size()));
+        AZ_CUDA(cudaMemcpy(c->dSgp4Orig.p, t.sgp4Orig.data(), t.sgp4Orig.size() * 4, cudaMemcpyHostToDevice));
+        std::vector<uint32_t> ident(t.sgp4Orig.size());
+        for (size_t i = 0; i < ident.size(); ++i) ident[i] = (uint32_t)std::min<size_t>(i, t.nSgp4 - 1);
+        AZ_CUDA(c->dIdentity.reserve(ident.size()));
+        AZ_CUDA(cudaMemcpy(c->dIdentity.p, ident.data(), ident.size() * 4, cudaMemcpyHostToDevice));
+        int32_t rc = upload_toff(c);
+        if (rc != ASTROZ_OK) return rc;
+    }
+    if (t.nSdp4) {
+        AZ_CUDA(c->dSdp4.reserve(t.nSdp4));
+        AZ_CUDA(cudaMemcpy(c->dSdp4.p, t.sdp4.data(), t.nSdp4 * sizeof(az::Sdp4Sat), cudaMemcpyHostToDevice));
+        AZ_CUDA(c->dSdp4Orig.reserve(t.nSdp4));
+        AZ_CUDA(cudaMemcpy(c->dSdp4Orig.p, t.sdp4Orig.data(), t.nSdp4 * 4, cudaMemcpyHostToDevice));
+    }
+    if (const char *v = std::getenv("ASTROZ_SGP4_VARIANT")) c->variant = std::atoi(v);
+    if (const char *v = std::getenv("ASTROZ_D2H_CHUNKS")) c->chunks = std::max(1, std::min(64, std::atoi(v)));
+    return ASTROZ_OK;
+}
+
+// host staging for the time axis; waits for the previous call's async upload before reuse
+int32_t reserve_time(Constellation *c, size_t nt) {
+    if (c->timePending) {
+        AZ_CUDA(cudaEventSynchronize(c->timeCopied));
+        c->timePending = false;
+    }
+    if (nt * 4 > c->hTimeCap) {
+        if (c->hTime) cudaFreeHost(c->hTime);
+        c->hTime = nullptr;
+        c->hTimeCap = 0;
+        AZ_CUDA(cudaMallocHost(&c->hTime, nt * 4 * 8));
+        c->hTimeCap = nt * 4;
+    }
+    AZ_CUDA(c->dTime.reserve(nt * 4));
+    return ASTROZ_OK;
+}
+
+int32_t ensure_lattice(Constellation *c, int nodes, cudaStream_t s) {
+    nodes = std::min(std::max(nodes, 2), 16384);
+    if (nodes <= c->latticeNodes) return ASTROZ_OK;
+    nodes = std::max(nodes, 32);
+    AZ_CUDA(cudaStreamSynchronize(s));  // a previous launch may still read the old lattice
+    AZ_CUDA(c->dLattice.reserve((size_t)c->cat.nSdp4 * 2 * nodes));
+    AZ_CUDA(az::launch_sdp4_lattice(c->dSdp4.p, c->cat.nSdp4, c->dLattice.p, nodes, s));
+    c->latticeNodes = nodes;
+    return ASTROZ_OK;
+}
+
+struct Launch {  // one grid pass over (satellite range) x (time range)
+    uint32_t tile0 = 0, tileCount = 0;  // near-earth tiles
+    bool deepSpace = true;              // include the deep-space satellites
+    uint32_t t0 = 0, nt = 0;            // epoch range
+};
+
+// Queue the kernels for `L` on stream s.  Time arrays must already be on the device.
+int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *dPos, double *dVel, uint8_t *dStatus,
+                   int mode, int layout, uint32_t outNumSats, uint32_t outSatOffset, cudaStream_t s, bool timeIt) {
+    const az::CatalogTables &t = c->cat;
+    const size_t tcap = c->dTime.cap / 4;
+    az::GridArgs a;
+    a.g = c->g;
+    a.nTimes = (layout == 0) ? ntTotal : L.nt;  // satellite-major rows are ntTotal long
+    a.outNumSats = outNumSats;
+    a.tbase = c->dTime.p + L.t0;
+    a.jdFull = c->dTime.p + tcap + L.t0;
+    a.gsin = c->dTime.p + 2 * tcap + L.t0;
+    a.gcos = c->dTime.p + 3 * tcap + L.t0;
+    // outputs: rows are shifted by outSatOffset, epochs by t0
+    size_t shift;
+    if (layout == 0) shift = ((size_t)outSatOffset * ntTotal + L.t0) * 3;
+    else shift = ((size_t)L.t0 * outNumSats + outSatOffset) * 3;
+    a.pos = dPos + shift;
+    a.vel = dVel ? dVel + shift : nullptr;
+    a.status = dStatus ? dStatus + (size_t)outSatOffset * ntTotal + L.t0 : nullptr;
+    if (layout == 0 && L.nt != ntTotal) {
+        g_lastError = "internal: satellite-major launches cover the whole time axis";
+        return ASTROZ_UNKNOWN;
+    }
+    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    if (L.tileCount && t.nSgp4) {
+        az::GridArgs k1 = a;
+        k1.sgp4Tiles = c->dTiles.p + (size_t)L.tile0 * az::kSgp4TileDoubles;
+        k1.toff = c->dToff.p + (size_t)L.tile0 * az::kTileSats;
+        k1.orig = c->dSgp4Orig.p + (size_t)L.tile0 * az::kTileSats;
+        const uint32_t first = L.tile0 * az::kTileSats;
+        k1.nSats = std::min<uint32_t>(t.nSgp4 - first, L.tileCount * az::kTileSats);
+        AZ_CUDA(az::launch_sgp4_grid(k1, mode, layout, s, c->variant));
+    }
+    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    if (L.deepSpace && t.nSdp4) {
+        az::GridArgs k2 = a;
+        k2.sdp4 = c->dSdp4.p;
+        k2.orig = c->dSdp4Orig.p;
+        k2.nSats = t.nSdp4;
+        k2.lattice = c->dLattice.p;
+        k2.latticeNodes = c->latticeNodes;
+        AZ_CUDA(az::launch_sdp4_grid(k2, mode, layout, s));
+    }
+    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    return ASTROZ_OK;
+}
+
+// Build the time axis on the host exactly as the reference does (src/Constellation.zig:266-284) and
+// queue its upload on s.
+int32_t upload_time_axis(Constellation *c, const double *jd, const double *fr, uint32_t nt, int mode, cudaStream_t s,
+                         double *jdMin, double *jdMax) {
+    int32_t rc = reserve_time(c, nt);
+    if (rc != ASTROZ_OK) return rc;
+    const size_t cap = c->dTime.cap / 4;
+    double *tb = c->hTime, *jf = c->hTime + nt, *gs = c->hTime + 2 * (size_t)nt, *gc = c->hTime + 3 * (size_t)nt;
+    double lo = INFINITY, hi = -INFINITY;
+    for (uint32_t t = 0; t < nt; ++t) {
+        const double j = jd[t] + fr[t];
+        jf[t] = j;
+        tb[t] = (j - c->cat.referenceEpochJd) * 1440.0;
+        lo = std::min(lo, j);
+        hi = std::max(hi, j);
+        if (mode != 0) {
+            const double gm = az::julian_to_gmst(j);
+            gs[t] = std::sin(gm);
+            gc[t] = std::cos(gm);
+        }
+    }
+    *jdMin = lo;
+    *jdMax = hi;
+    const int arrays = (mode != 0) ? 4 : 2;
+    for (int k = 0; k < arrays; ++k)
+        AZ_CUDA(cudaMemcpyAsync(c->dTime.p + k * cap, c->hTime + (size_t)k * nt, (size_t)nt * 8, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaEventRecord(c->timeCopied, s));
+    c->timePending = true;
+    return ASTROZ_OK;
+}
+
+int32_t prepare_deep_space(Constellation *c, double jdMin, double jdMax, cudaStream_t s) {
+    if (c->cat.nSdp4 == 0) return ASTROZ_OK;
+    double eMin = INFINITY, eMax = -INFINITY;
+    for (const az::Sdp4Sat &r : c->cat.sdp4) {
+        eMin = std::min(eMin, r.epochJd);
+        eMax = std::max(eMax, r.epochJd);
+    }
+    const double reach = std::max(std::fabs((jdMax - eMin) * 1440.0), std::fabs((jdMin - eMax) * 1440.0));
+    return ensure_lattice(c, (int)std::floor(reach / az::kStepp) + 2, s);
+}
+
+int32_t check_args(Constellation *c, const void *jd, const void *fr, const void *pos, int mode, int layout) {
+    if (!c || !jd || !fr || !pos) return ASTROZ_NULL_POINTER;
+    if (mode < 0 || mode > 2 || layout < 0 || layout > 1) {
+        g_lastError = "invalid output mode / layout";
+        return ASTROZ_VALUE_ERROR;
+    }
+    return ASTROZ_OK;
+}
+
+struct Sgp4Single {
+    Constellation *c = nullptr;
+    double epochJd = 0;
+    bool deep = false;
+};
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+#pragma GCC visibility push(default)
+
+uint32_t astroz_cuda_version(void) { return (0u << 16) | (1u << 8) | 0u; }
+
+int32_t astroz_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *astroz_cuda_last_error(void) { return g_lastError.c_str(); }
+
+void *astroz_cuda_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 8) != cudaSuccess) return nullptr;
+    return p;
+}
+void astroz_cuda_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int32_t astroz_cuda_constellation_create(const char *const *line1, const char *const *line2, uint32_t n, int32_t grav,
+                                         int32_t device, astroz_constellation_t *out) {
+    if (!out || (n && (!line1 || !line2))) return ASTROZ_NULL_POINTER;
+    *out = nullptr;
+    Constellation *c = new (std::nothrow) Constellation();
+    if (!c) return ASTROZ_ALLOC_FAILED;
+    int rc = az::build_catalog(line1, line2, n, grav, c->cat);
+    if (rc != az::kOk) {
+        delete c;
+        return status_to_code(rc);
+    }
+    int32_t e = finish_create(c, device);
+    if (e != ASTROZ_OK) {
+        delete c;
+        return e;
+    }
+    *out = c;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_create_from_text(const char *text, size_t len, int32_t grav, int32_t device,
+                                                   astroz_constellation_t *out) {
+    if (!text || !out) return ASTROZ_NULL_POINTER;
+    std::vector<std::string> l1, l2;
+    az::split_tle_text(text, len, l1, l2);
+    std::vector<const char *> p1(l1.size()), p2(l2.size());
+    for (size_t i = 0; i < l1.size(); ++i) {
+        p1[i] = l1[i].c_str();
+        p2[i] = l2[i].c_str();
+    }
+    return astroz_cuda_constellation_create(p1.data(), p2.data(), (uint32_t)l1.size(), grav, device, out);
+}
+
+void astroz_cuda_constellation_free(astroz_constellation_t h) { delete static_cast<Constellation *>(h); }
+
+int32_t astroz_cuda_constellation_counts(astroz_constellation_t h, uint32_t *n, uint32_t *ns, uint32_t *nd) {
+    if (!h) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    if (n) *n = c->cat.n;
+    if (ns) *ns = c->cat.nSgp4;
+    if (nd) *nd = c->cat.nSdp4;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_epochs(astroz_constellation_t h, double *epochs) {
+    if (!h || !epochs) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    std::memcpy(epochs, c->cat.epochs.data(), c->cat.epochs.size() * 8);
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_classes(astroz_constellation_t h, int32_t *classes) {
+    if (!h || !classes) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    std::memcpy(classes, c->cat.classes.data(), c->cat.classes.size() * 4);
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_get_reference_epoch(astroz_constellation_t h, double *jd) {
+    if (!h || !jd) return ASTROZ_NULL_POINTER;
+    *jd = static_cast<Constellation *>(h)->cat.referenceEpochJd;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_set_reference_epoch(astroz_constellation_t h, double jd) {
+    if (!h) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    AZ_CUDA(cudaSetDevice(c->device));
+    AZ_CUDA(cudaStreamSynchronize(c->stream));
+    c->cat.referenceEpochJd = jd;
+    return upload_toff(c);
+}
+
+int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, const double *jd, const double *fr,
+                                                   uint32_t n_times, double *d_pos, double *d_vel, uint8_t *d_status,
+                                                   int32_t mode, int32_t layout, uint32_t out_num_sats,
+                                                   uint32_t out_sat_offset, void *stream) {
+    Constellation *c = static_cast<Constellation *>(h);
+    int32_t rc = check_args(c, jd, fr, d_pos, mode, layout);
+    if (rc != ASTROZ_OK) return rc;
+    if (n_times == 0 || c->cat.n == 0) return ASTROZ_OK;
+    if (out_num_sats < out_sat_offset + c->cat.n) {  // src/Constellation.zig:255-257 reports a short buffer this way
+        g_lastError = "output block smaller than numSatellites rows";
+        return ASTROZ_DECAYED;
+    }
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    double jdMin, jdMax;
+    rc = upload_time_axis(c, jd, fr, n_times, mode, s, &jdMin, &jdMax);
+    if (rc != ASTROZ_OK) return rc;
+    rc = prepare_deep_space(c, jdMin, jdMax, s);
+    if (rc != ASTROZ_OK) return rc;
+    Launch L;
+    L.tileCount = c->cat.sgp4Tiles_count();
+    L.nt = n_times;
+    rc = queue_grid(c, L, n_times, d_pos, d_vel, d_status, mode, layout, out_num_sats, out_sat_offset, s, true);
+    c->timed = (rc == ASTROZ_OK);
+    return rc;
+}
+
+int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const double *jd, const double *fr,
+                                            uint32_t n_times, double *pos, double *vel, int32_t mode, int32_t layout) {
+    Constellation *c = static_cast<Constellation *>(h);
+    int32_t rc = check_args(c, jd, fr, pos, mode, layout);
+    if (rc != ASTROZ_OK) return rc;
+    const uint32_t n = c->cat.n;
+    if (n_times == 0 || n == 0) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    const size_t total = (size_t)n * n_times * 3;
+    AZ_CUDA(c->dPos.reserve(total));
+    if (vel) AZ_CUDA(c->dVel.reserve(total));
+    double *dPos = c->dPos.p, *dVel = vel ? c->dVel.p : nullptr;
+    cudaStream_t s = c->stream;
+    double jdMin, jdMax;
+    rc = upload_time_axis(c, jd, fr, n_times, mode, s, &jdMin, &jdMax);
+    if (rc != ASTROZ_OK) return rc;
+    rc = prepare_deep_space(c, jdMin, jdMax, s);
+    if (rc != ASTROZ_OK) return rc;
+
+    // Pipeline: the grid is cut into chunks whose output is one contiguous block of the result, so the
+    // device->host copy of chunk i (copy stream) overlaps the kernels of chunk i+1 (compute stream).
+    const uint32_t tiles = c->cat.sgp4Tiles_count();
+    const bool bySat = (layout == 0) && c->cat.nSdp4 == 0;  // near-earth rows are the identity map
+    const bool byTime = (layout == 1);
+    uint32_t units = bySat ? tiles : (byTime ? n_times : 1);
+    uint32_t nChunks = (bySat || byTime) ? std::min<uint32_t>((uint32_t)c->chunks, units) : 1;
+    if (total * 8 < (8u << 20)) nChunks = 1;
+    const uint32_t per = (units + nChunks - 1) / nChunks;
+    for (uint32_t k = 0; k < nChunks; ++k) {
+        const uint32_t u0 = k * per, u1 = std::min(units, u0 + per);
+        if (u0 >= u1) break;
+        Launch L;
+        size_t off, cnt;
+        if (bySat) {
+            L.tile0 = u0; L.tileCount = u1 - u0; L.deepSpace = false; L.t0 = 0; L.nt = n_times;
+            const size_t r0 = (size_t)u0 * az::kTileSats, r1 = std::min<size_t>(n, (size_t)u1 * az::kTileSats);
+            off = r0 * n_times * 3;
+            cnt = (r1 - r0) * n_times * 3;
+        } else if (byTime) {
+            L.tile0 = 0; L.tileCount = tiles; L.deepSpace = true; L.t0 = u0; L.nt = u1 - u0;
+            off = (size_t)u0 * n * 3;
+            cnt = (size_t)(u1 - u0) * n * 3;
+        } else {
+            L.tile0 = 0; L.tileCount = tiles; L.deepSpace = true; L.t0 = 0; L.nt = n_times;
+            off = 0;
+            cnt = total;
+        }
+        rc = queue_grid(c, L, n_times, dPos, dVel, nullptr, mode, layout, n, 0, s, k == 0);
+        if (rc != ASTROZ_OK) return rc;
+        AZ_CUDA(cudaEventRecord(c->chunkDone[k], s));
+        AZ_CUDA(cudaStreamWaitEvent(c->copyStream, c->chunkDone[k], 0));
+        AZ_CUDA(cudaMemcpyAsync(pos + off, dPos + off, cnt * 8, cudaMemcpyDeviceToHost, c->copyStream));
+        if (vel) AZ_CUDA(cudaMemcpyAsync(vel + off, dVel + off, cnt * 8, cudaMemcpyDeviceToHost, c->copyStream));
+    }
+    c->timed = true;
+    AZ_CUDA(cudaStreamSynchronize(c->copyStream));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_reset_carry(astroz_constellation_t h) { return h ? ASTROZ_OK : ASTROZ_NULL_POINTER; }
+
+int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h) {
+    if (!h) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    AZ_CUDA(cudaSetDevice(c->device));
+    AZ_CUDA(cudaStreamSynchronize(c->stream));
+    AZ_CUDA(cudaStreamSynchronize(c->copyStream));
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float ms[3]) {
+    if (!h || !ms) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (!c->timed) return ASTROZ_NOT_INITIALIZED;
+    AZ_CUDA(cudaSetDevice(c->device));
+    AZ_CUDA(cudaEventSynchronize(c->ev[3]));
+    AZ_CUDA(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
+    AZ_CUDA(cudaEventElapsedTime(&ms[2], c->ev[2], c->ev[3]));
+    return ASTROZ_OK;
+}
+
+// ---- stateless near-earth path -----------------------------------------------------------------
+static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t nt, const double *epoch_offsets,
+                                double *dPos, double *dVel, int mode, double reference_jd, int layout, cudaStream_t s) {
+    const uint32_t ns = c->cat.nSgp4;
+    const uint32_t padded = c->cat.sgp4Padded();
+    int32_t rc = reserve_time(c, nt);
+    if (rc != ASTROZ_OK) return rc;
+    const size_t cap = c->dTime.cap / 4;
+    double *tb = c->hTime, *gs = c->hTime + 2 * (size_t)nt, *gc = c->hTime + 3 * (size_t)nt;
+    for (uint32_t t = 0; t < nt; ++t) {
+        tb[t] = times[t];
+        if (mode != 0) {  // src/Constellation.zig:573-581
+            const double gm = az::julian_to_gmst(reference_jd + times[t] / 1440.0);
+            gs[t] = std::sin(gm);
+            gc[t] = std::cos(gm);
+        }
+    }
+    AZ_CUDA(cudaMemcpyAsync(c->dTime.p, tb, (size_t)nt * 8, cudaMemcpyHostToDevice, s));
+    if (mode != 0) {
+        AZ_CUDA(cudaMemcpyAsync(c->dTime.p + 2 * cap, gs, (size_t)nt * 8, cudaMemcpyHostToDevice, s));
+        AZ_CUDA(cudaMemcpyAsync(c->dTime.p + 3 * cap, gc, (size_t)nt * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (padded > c->hToffCap) {
+        if (c->hToffCall) cudaFreeHost(c->hToffCall);
+        c->hToffCall = nullptr;
+        AZ_CUDA(cudaMallocHost(&c->hToffCall, (size_t)padded * 8));
+        c->hToffCap = padded;
+    }
+    for (uint32_t i = 0; i < padded; ++i) c->hToffCall[i] = epoch_offsets[std::min(i, ns - 1)];
+    AZ_CUDA(c->dToffCall.reserve(padded));
+    AZ_CUDA(cudaMemcpyAsync(c->dToffCall.p, c->hToffCall, (size_t)padded * 8, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaEventRecord(c->timeCopied, s));
+    c->timePending = true;
+
+    az::GridArgs a;
+    a.g = c->g;
+    a.sgp4Tiles = c->dTiles.p;
+    a.toff = c->dToffCall.p;
+    a.orig = c->dIdentity.p;  // satellite i -> output row i (src/Constellation.zig:561-565)
+    a.nSats = ns;
+    a.tbase = c->dTime.p;
+    a.gsin = c->dTime.p + 2 * cap;
+    a.gcos = c->dTime.p + 3 * cap;
+    a.nTimes = nt;
+    a.pos = dPos;
+    a.vel = dVel;
+    a.outNumSats = ns;
+    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    AZ_CUDA(az::launch_sgp4_grid(a, mode, layout, s, c->variant));
+    AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = true;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                               const double *epoch_offsets, double *d_pos, double *d_vel, int32_t mode,
+                                               double reference_jd, int32_t layout, void *stream) {
+    Constellation *c = static_cast<Constellation *>(h);
+    int32_t rc = check_args(c, times, epoch_offsets, d_pos, mode, layout);
+    if (rc != ASTROZ_OK) return rc;
+    if (n_times == 0 || c->cat.nSgp4 == 0) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    return sgp4_into_common(c, times, n_times, epoch_offsets, d_pos, d_vel, mode, reference_jd, layout, s);
+}
+
+int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                        const double *epoch_offsets, double *pos, double *vel, int32_t mode,
+                                        double reference_jd, int32_t layout) {
+    Constellation *c = static_cast<Constellation *>(h);
+    int32_t rc = check_args(c, times, epoch_offsets, pos, mode, layout);
+    if (rc != ASTROZ_OK) return rc;
+    const uint32_t ns = c->cat.nSgp4;
+    if (n_times == 0 || ns == 0) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    const size_t total = (size_t)ns * n_times * 3;
+    AZ_CUDA(c->dPos.reserve(total));
+    if (vel) AZ_CUDA(c->dVel.reserve(total));
+    rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode, reference_jd,
+                          layout, c->stream);
+    if (rc != ASTROZ_OK) return rc;
+    AZ_CUDA(cudaMemcpyAsync(pos, c->dPos.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (vel) AZ_CUDA(cudaMemcpyAsync(vel, c->dVel.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
+    AZ_CUDA(cudaStreamSynchronize(c->stream));
+    return ASTROZ_OK;
+}
+
+// ---- single satellite ----------------------------------------------------------------------------
+int32_t astroz_cuda_sgp4_init(const char *line1, const char *line2, int32_t grav, int32_t device, astroz_sgp4_t *out) {
+    if (!line1 || !line2 || !out) return ASTROZ_NULL_POINTER;
+    *out = nullptr;
+    astroz_constellation_t ch = nullptr;
+    const char *l1[1] = {line1}, *l2[1] = {line2};
+    int32_t rc = astroz_cuda_constellation_create(l1, l2, 1, grav, device, &ch);
+    if (rc != ASTROZ_OK) return rc;
+    Sgp4Single *s = new (std::nothrow) Sgp4Single();
+    if (!s) {
+        astroz_cuda_constellation_free(ch);
+        return ASTROZ_ALLOC_FAILED;
+    }
+    s->c = static_cast<Constellation *>(ch);
+    s->epochJd = s->c->cat.epochs[0];
+    s->deep = s->c->cat.nSdp4 == 1;
+    *out = s;
+    return ASTROZ_OK;
+}
+
+void astroz_cuda_sgp4_free(astroz_sgp4_t h) {
+    Sgp4Single *s = static_cast<Sgp4Single *>(h);
+    if (!s) return;
+    delete s->c;
+    delete s;
+}
+
+int32_t astroz_cuda_sgp4_is_deep_space(astroz_sgp4_t h) { return h && static_cast<Sgp4Single *>(h)->deep ? 1 : 0; }
+
+int32_t astroz_cuda_sgp4_epoch(astroz_sgp4_t h, double *epoch_jd) {
+    if (!h || !epoch_jd) return ASTROZ_NULL_POINTER;
+    *epoch_jd = static_cast<Sgp4Single *>(h)->epochJd;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, double *results, uint32_t count) {
+    Sgp4Single *s = static_cast<Sgp4Single *>(h);
+    if (!s || !times || !results) return ASTROZ_NULL_POINTER;
+    if (count == 0) return ASTROZ_OK;
+    Constellation *c = s->c;
+    AZ_CUDA(cudaSetDevice(c->device));
+    std::vector<double> pos((size_t)count * 3), vel((size_t)count * 3);
+    int32_t rc;
+    if (!s->deep) {
+        const double zero = 0.0;
+        rc = astroz_cuda_sgp4_propagate_into(c, times, count, &zero, pos.data(), vel.data(), ASTROZ_MODE_TEME, 0.0,
+                                             ASTROZ_LAYOUT_SATELLITE_MAJOR);
+        if (rc != ASTROZ_OK) return rc;
+    } else {
+        // deep space: minutes since epoch go to the kernel directly (no Julian-date round trip)
+        int32_t rt = reserve_time(c, count);
+        if (rt != ASTROZ_OK) return rt;
+        double reach = 0.0;
+        for (uint32_t i = 0; i < count; ++i) {
+            c->hTime[i] = times[i];
+            reach = std::max(reach, std::fabs(times[i]));
+        }
+        cudaStream_t st = c->stream;
+        AZ_CUDA(cudaMemcpyAsync(c->dTime.p, c->hTime, (size_t)count * 8, cudaMemcpyHostToDevice, st));
+        AZ_CUDA(cudaEventRecord(c->timeCopied, st));
+        c->timePending = true;
+        rc = ensure_lattice(c, (int)std::floor(reach / az::kStepp) + 2, st);
+        if (rc != ASTROZ_OK) return rc;
+        const size_t total = (size_t)count * 3;
+        DevBuf<uint8_t> dSt;
+        AZ_CUDA(c->dPos.reserve(total));
+        AZ_CUDA(c->dVel.reserve(total));
+        AZ_CUDA(dSt.reserve(count));
+        az::GridArgs a;
+        a.g = c->g;
+        a.sdp4 = c->dSdp4.p;
+        a.orig = c->dSdp4Orig.p;
+        a.nSats = 1;
+        a.lattice = c->dLattice.p;
+        a.latticeNodes = c->latticeNodes;
+        a.tsince = c->dTime.p;
+        a.nTimes = count;
+        a.pos = c->dPos.p;
+        a.vel = c->dVel.p;
+        a.status = dSt.p;
+        a.outNumSats = 1;
+        std::vector<uint8_t> cell(count);
+        cudaError_t e = az::launch_sdp4_grid(a, ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(pos.data(), c->dPos.p, total * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(vel.data(), c->dVel.p, total * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cell.data(), dSt.p, count, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        dSt.release();
+        if (e != cudaSuccess) return cuda_fail(e, "single-satellite deep-space propagate");
+        rc = ASTROZ_OK;
+        for (uint32_t i = 0; i < count; ++i)
+            if (cell[i] != 0) rc = status_to_code(cell[i]);  // failing cells stay zero-filled; last failure reported
+    }
+    for (uint32_t i = 0; i < count; ++i) {
+        double *r = results + (size_t)i * 6;
+        r[0] = pos[i * 3]; r[1] = pos[i * 3 + 1]; r[2] = pos[i * 3 + 2];
+        r[3] = vel[i * 3]; r[4] = vel[i * 3 + 1]; r[5] = vel[i * 3 + 2];
+    }
+    return rc;
+}
+
+int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3], double vel[3]) {
+    if (!h || !pos || !vel) return ASTROZ_NULL_POINTER;
+    double r[6];
+    int32_t rc = astroz_cuda_sgp4_propagate_batch(h, &tsince, r, 1);
+    std::memcpy(pos, r, 24);
+    std::memcpy(vel, r + 3, 24);
+    return rc;
+}
+
+int32_t astroz_cuda_fp64_peak(int32_t device, double *tflops) {
+    if (!tflops) return ASTROZ_NULL_POINTER;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        g_lastError = "no CUDA device available";
+        return ASTROZ_NO_DEVICE;
+    }
+    AZ_CUDA(cudaSetDevice(device));
+    double flops = 0;
+    AZ_CUDA(az::measure_fp64_peak(&flops));
+    *tflops = flops * 1e-12;
+    return ASTROZ_OK;
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,316 @@
+// az_kernels.cu -- hand-written sm_100a kernels of the batch SGP4/SDP4 path.
+//
+//   K1  sgp4_grid_kernel    near-earth (n_sats x n_times) grid   -- replaces sgp4Batch8 + the
+//                           Constellation hot loop (src/simdKernels.zig:9-13, src/Constellation.zig:405-434,478-509)
+//   K2a sdp4_lattice_kernel resonance checkpoints on the 720-min lattice (src/Sdp4.zig:787-801)
+//   K2  sdp4_grid_kernel    deep-space grid -- replaces sdp4Batch8 (src/simdKernels.zig:15-19,
+//                           src/Constellation.zig:448-476)
+//
+// Mapping (K1): a CTA owns one 8-satellite tile of the element table and one stripe of epochs.  The
+// tile (2,112 B, SoA) is staged into shared memory with a single TMA bulk copy (cp.async.bulk +
+// mbarrier).  Each warp takes satellites of the tile in turn; its 32 lanes are 32 consecutive epochs of
+// that satellite, so every per-satellite constant is a conflict-free shared-memory broadcast, the drag
+// model branch (isimp) is warp-uniform, and the Kepler iteration count is near-uniform across the warp
+// (same eccentricity).  All arithmetic is fp64 on the CUDA cores; there is no contraction to give the
+// tensor cores.
+#include "az_kernels.cuh"
+
+#include <algorithm>
+
+namespace az {
+
+// ---------------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier helpers (PTX ISA: cp.async.bulk, mbarrier)
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy performed by the TMA unit; completion is signalled on `bar` in bytes
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------
+// output stage shared by K1 / K2: frame conversion + store
+// ---------------------------------------------------------------------------------------------------
+template <int kLayout, int kMode, bool kVel>
+__device__ __forceinline__ void store_cell(const GridArgs &a, uint32_t row, uint32_t t, CellOut &o) {
+    if (kMode != 0) {
+        const double sg = __ldg(a.gsin + t), cg = __ldg(a.gcos + t);
+        eci_to_ecef(o.rx, o.ry, sg, cg);
+        if (kVel) eci_to_ecef(o.vx, o.vy, sg, cg);  // pure rotation, no omega x r (src/Constellation.zig:501-506)
+        if (kMode == 2) ecef_to_geodetic(o.rx, o.ry, o.rz);
+    }
+    const size_t idx = (kLayout == 0) ? ((size_t)row * a.nTimes + t) * 3 : ((size_t)t * a.outNumSats + row) * 3;
+    double *p = a.pos + idx;
+    __stcs(p, o.rx);
+    __stcs(p + 1, o.ry);
+    __stcs(p + 2, o.rz);
+    if (kVel) {
+        double *v = a.vel + idx;
+        __stcs(v, o.vx);
+        __stcs(v + 1, o.vy);
+        __stcs(v + 2, o.vz);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1: near-earth grid
+// ---------------------------------------------------------------------------------------------------
+template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(const GridArgs a) {
+    __shared__ __align__(128) double tile[kSgp4TileDoubles];
+    __shared__ __align__(8) uint64_t bar;
+
+    const uint32_t tileIdx = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, kSgp4TileBytes);
+        tma_bulk_g2s(tile, a.sgp4Tiles + (size_t)tileIdx * kSgp4TileDoubles, kSgp4TileBytes, &bar);
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t0 = blockIdx.y * kStripe;
+    const uint32_t t1 = min(t0 + (uint32_t)kStripe, a.nTimes);
+    mbar_wait(&bar, 0);
+
+#pragma unroll 1
+    for (int sl = warp; sl < kTileSats; sl += kWarps) {
+        const uint32_t sat = tileIdx * kTileSats + sl;
+        if (sat >= a.nSats) break;  // padding lanes of the last tile (src/Constellation.zig:146,493)
+        const double *colBase = tile + sl;
+        auto col = [colBase](int i) { return colBase[i * kTileSats]; };
+        const double toff = __ldg(a.toff + sat);
+        const uint32_t row = __ldg(a.orig + sat);
+#pragma unroll 1
+        for (uint32_t t = t0 + lane; t < t1; t += 32) {
+            const double ts = __ldg(a.tbase + t) + toff;  // src/Constellation.zig:425
+            CellOut o;
+            sgp4_cell(col, ts, a.g, o);
+            if (a.status) a.status[(size_t)row * a.nTimes + t] = (o.mrt < 1.0) ? 1 : 0;
+            store_cell<kLayout, kMode, kVel>(a, row, t, o);
+        }
+    }
+}
+
+struct Sgp4Variant {
+    const char *name;
+    int warps, stripe, minBlocks;
+};
+static const Sgp4Variant kVariants[] = {
+    {"w4_s256_b4", 4, 256, 4}, {"w4_s256_b3", 4, 256, 3}, {"w8_s256_b2", 8, 256, 2},
+    {"w4_s128_b5", 4, 128, 5}, {"w4_s512_b4", 4, 512, 4}, {"w8_s128_b3", 8, 128, 3},
+    {"w2_s256_b8", 2, 256, 8}, {"w4_s256_b2", 4, 256, 2},
+};
+int sgp4_variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
+const char *sgp4_variant_name(int v) { return (v >= 0 && v < sgp4_variant_count()) ? kVariants[v].name : "?"; }
+
+template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks>
+static cudaError_t launch_k1(const GridArgs &a, cudaStream_t stream) {
+    const uint32_t tiles = (a.nSats + kTileSats - 1) / kTileSats;
+    const uint32_t stripes = (a.nTimes + kStripe - 1) / kStripe;
+    if (tiles == 0 || stripes == 0) return cudaSuccess;
+    dim3 grid(tiles, stripes);
+    sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks><<<grid, kWarps * 32, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <int kLayout, int kMode, bool kVel>
+static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int variant) {
+    if (kLayout == 0 && kMode == 0 && kVel) {  // tuning variants exist for the headline specialisation only
+        switch (variant) {
+            case 1: return launch_k1<0, 0, true, 4, 256, 3>(a, stream);
+            case 2: return launch_k1<0, 0, true, 8, 256, 2>(a, stream);
+            case 3: return launch_k1<0, 0, true, 4, 128, 5>(a, stream);
+            case 4: return launch_k1<0, 0, true, 4, 512, 4>(a, stream);
+            case 5: return launch_k1<0, 0, true, 8, 128, 3>(a, stream);
+            case 6: return launch_k1<0, 0, true, 2, 256, 8>(a, stream);
+            case 7: return launch_k1<0, 0, true, 4, 256, 2>(a, stream);
+            default: break;
+        }
+    }
+    return launch_k1<kLayout, kMode, kVel, 4, 256, 4>(a, stream);
+}
+
+cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant) {
+    const bool vel = a.vel != nullptr;
+#define AZ_K1(L, M)                                                               \
+    if (layout == L && mode == M)                                                 \
+        return vel ? launch_k1_variant<L, M, true>(a, stream, variant)            \
+                   : launch_k1_variant<L, M, false>(a, stream, variant);
+    AZ_K1(0, 0) AZ_K1(0, 1) AZ_K1(0, 2) AZ_K1(1, 0) AZ_K1(1, 1) AZ_K1(1, 2)
+#undef AZ_K1
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2a: resonance lattice.  thread = (deep-space satellite, direction); node k holds the integrator
+// state after k steps of +-720 min from atime = 0 (src/Sdp4.zig:787-801, carry == fresh integration
+// by src/Sdp4Batch.zig:603-629).
+// ---------------------------------------------------------------------------------------------------
+__global__ void sdp4_lattice_kernel(const Sdp4Sat *__restrict__ sats, uint32_t nSats, double2 *__restrict__ lattice,
+                                    int nodes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nSats * 2) return;
+    const uint32_t sat = i >> 1;
+    const Sdp4Sat e = sats[sat];
+    const double delt = (i & 1) ? -kStepp : kStepp;
+    double2 *out = lattice + (size_t)i * nodes;
+    double xli = e.xlamo, xni = e.no, atime = 0.0;
+    out[0] = make_double2(xli, xni);
+    if (e.irez == 0) return;
+#pragma unroll 1
+    for (int k = 1; k < nodes; ++k) {
+        resonance_step(e, xli, xni, atime, delt);
+        out[k] = make_double2(xli, xni);
+    }
+}
+
+cudaError_t launch_sdp4_lattice(const Sdp4Sat *sats, uint32_t nSats, double2 *lattice, int nodes, cudaStream_t stream) {
+    if (nSats == 0) return cudaSuccess;
+    const uint32_t threads = 64, total = nSats * 2;
+    sdp4_lattice_kernel<<<(total + threads - 1) / threads, threads, 0, stream>>>(sats, nSats, lattice, nodes);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: deep-space grid.  CTA = one satellite x one stripe of epochs; the satellite record sits in shared
+// memory; a lane is one epoch, so the resonance class branch (irez) is uniform across the CTA.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSdp4Threads = 128;
+constexpr int kSdp4Stripe = 512;
+
+template <int kLayout, int kMode, bool kVel>
+__global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridArgs a) {
+    __shared__ Sdp4Sat e;
+    const uint32_t sat = blockIdx.x;
+    {
+        const double *src = reinterpret_cast<const double *>(a.sdp4 + sat);
+        double *dst = reinterpret_cast<double *>(&e);
+        for (int i = threadIdx.x; i < (int)(sizeof(Sdp4Sat) / 8); i += kSdp4Threads) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const uint32_t row = __ldg(a.orig + sat);
+    const uint32_t t0 = blockIdx.y * kSdp4Stripe;
+    const uint32_t t1 = min(t0 + (uint32_t)kSdp4Stripe, a.nTimes);
+#pragma unroll 1
+    for (uint32_t t = t0 + threadIdx.x; t < t1; t += kSdp4Threads) {
+        const double ts = a.tsince ? __ldg(a.tsince + t)
+                                   : (__ldg(a.jdFull + t) - e.epochJd) * 1440.0;  // src/Constellation.zig:465
+        double xli = e.xlamo, xni = e.no, atime = 0.0;
+        if (e.irez != 0) {
+            const int node = resonance_node(ts);
+            const int have = min(node, a.latticeNodes - 1);
+            const double2 st = __ldg(a.lattice + ((size_t)sat * 2 + (ts > 0.0 ? 0 : 1)) * a.latticeNodes + have);
+            const double delt = ts > 0.0 ? kStepp : -kStepp;
+            xli = st.x;
+            xni = st.y;
+            atime = delt * (double)have;
+            for (int k = have; k < node; ++k) resonance_step(e, xli, xni, atime, delt);  // beyond the lattice
+        }
+        CellOut o;
+        const int st = sdp4_cell(e, ts, xli, xni, atime, a.g, o);
+        if (a.status) a.status[(size_t)row * a.nTimes + t] = (uint8_t)st;
+        if (st != 0) {  // zero fill, per satellite (src/Constellation.zig:468-471,511-528 does it per batch of 8)
+            const size_t idx = (kLayout == 0) ? ((size_t)row * a.nTimes + t) * 3 : ((size_t)t * a.outNumSats + row) * 3;
+            a.pos[idx] = a.pos[idx + 1] = a.pos[idx + 2] = 0.0;
+            if (kVel) a.vel[idx] = a.vel[idx + 1] = a.vel[idx + 2] = 0.0;
+        } else {
+            store_cell<kLayout, kMode, kVel>(a, row, t, o);
+        }
+    }
+}
+
+template <int kLayout, int kMode, bool kVel>
+static cudaError_t launch_k2(const GridArgs &a, cudaStream_t stream) {
+    const uint32_t stripes = (a.nTimes + kSdp4Stripe - 1) / kSdp4Stripe;
+    if (a.nSats == 0 || stripes == 0) return cudaSuccess;
+    dim3 grid(a.nSats, stripes);
+    sdp4_grid_kernel<kLayout, kMode, kVel><<<grid, kSdp4Threads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sdp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream) {
+    const bool vel = a.vel != nullptr;
+#define AZ_K2(L, M) \
+    if (layout == L && mode == M) return vel ? launch_k2<L, M, true>(a, stream) : launch_k2<L, M, false>(a, stream);
+    AZ_K2(0, 0) AZ_K2(0, 1) AZ_K2(0, 2) AZ_K2(1, 0) AZ_K2(1, 1) AZ_K2(1, 2)
+#undef AZ_K2
+    return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp64 roofline denominator: dependent-chain-free DFMA loop, 8 independent accumulators per thread
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
+    double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 1234.5678) out[0] = s;  // keep the chain alive without a real store
+}
+
+cudaError_t measure_fp64_peak(double *flops) {
+    int dev = 0, sms = 0;
+    cudaError_t rc = cudaGetDevice(&dev);
+    if (rc != cudaSuccess) return rc;
+    rc = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (rc != cudaSuccess) return rc;
+    double *d = nullptr;
+    rc = cudaMalloc(&d, 8);
+    if (rc != cudaSuccess) return rc;
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        rc = cudaEventSynchronize(e1);
+        if (rc != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    if (rc != cudaSuccess) return rc;
+    *flops = 2.0 * 64.0 * (double)iters * (double)blocks * (double)threads / (best * 1e-3);
+    return cudaSuccess;
+}
+
+}  // namespace az

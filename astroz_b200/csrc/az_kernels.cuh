@@ -1,0 +1,48 @@
+// az_kernels.cuh -- launch interface of the grid kernels (internal to the library).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "az_device.cuh"
+
+namespace az {
+
+// Arguments of one (n_sats x n_times) grid launch.  All pointers are device pointers.
+struct GridArgs {
+    // near-earth table (K1) or deep-space records (K2)
+    const double *sgp4Tiles = nullptr;   // [tiles][kSgp4Cols][8]
+    const Sdp4Sat *sdp4 = nullptr;       // [nSats]
+    const double2 *lattice = nullptr;    // K2: [nSats][2][latticeNodes] (xli, xni) at atime = +-720*k
+    int latticeNodes = 0;
+    const uint32_t *orig = nullptr;      // output row of each table satellite (padded for K1)
+    uint32_t nSats = 0;                  // real satellites in the table
+    // time axis
+    const double *tbase = nullptr;       // K1: minutes of each epoch relative to the reference epoch
+    const double *toff = nullptr;        // K1: per-satellite (reference - epoch) * 1440, padded
+    const double *jdFull = nullptr;      // K2: jd + fr per epoch
+    const double *tsince = nullptr;      // K2: if set, minutes since epoch are taken from here instead
+    const double *gsin = nullptr;        // sin/cos(GMST) per epoch when mode != TEME
+    const double *gcos = nullptr;
+    uint32_t nTimes = 0;
+    // outputs
+    double *pos = nullptr;
+    double *vel = nullptr;               // nullable
+    uint8_t *status = nullptr;           // nullable, [outRow][nTimes]
+    uint32_t outNumSats = 0;             // row count of the output block (time-major stride)
+    GravConsts g{};
+};
+
+// K1: near-earth grid.  variant selects a tuning configuration (0 = default).
+cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant);
+// K2a: resonance lattice pre-pass (one thread per deep-space satellite, sequential 720-min steps).
+cudaError_t launch_sdp4_lattice(const Sdp4Sat *sats, uint32_t nSats, double2 *lattice, int nodes, cudaStream_t stream);
+// K2: deep-space grid.
+cudaError_t launch_sdp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream);
+// DFMA throughput microbenchmark: returns achieved fp64 FLOP/s (FMA = 2).
+cudaError_t measure_fp64_peak(double *flops);
+
+int sgp4_variant_count();
+const char *sgp4_variant_name(int variant);
+
+}  // namespace az

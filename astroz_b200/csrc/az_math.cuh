@@ -1,0 +1,190 @@
+// az_math.cuh -- fp64 device math for the SGP4/SDP4 grid kernels (sm_100a).
+//
+// Replaces src/simdMath.zig (sincosN :29-97, modTwoPiN :110-122, atan2N :124-177, pow15N :180-182,
+// pow23N :201-212) of the reference.  Design differences, all deliberate:
+//   * sincos: branch-free Cody-Waite (pi/2 in three parts, FMA) + fdlibm minimax kernels, ~1 ulp;
+//     no Payne-Hanek slow path (arguments here are bounded by |x| < ~1e5 rad: years of mean anomaly).
+//   * atan2 is never needed on the SGP4 path: the true-longitude unit vector (sinu, cosu) is already
+//     normalised, so the short-period rotation is applied with an angle-addition (see kernels).
+//   * reciprocal / rsqrt: MUFU seed (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64) + Newton steps in
+//     FMA form -- no special-case slow path, operands are O(1) by construction.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+// The per-cell cores are __host__ __device__ so tests/host_emul can run the *same arithmetic* on the
+// CPU in unit tests when no GPU is present.  The shipped library exposes no host propagation path.
+#define AZ_HD __host__ __device__ __forceinline__
+
+namespace az {
+
+AZ_HD int dbl_lo(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2loint(x);
+#else
+    uint64_t b; memcpy(&b, &x, 8); return (int)(uint32_t)b;
+#endif
+}
+AZ_HD double dbl_xor_hi(double x, unsigned mask) {  // flip bits of the high word (sign control)
+#ifdef __CUDA_ARCH__
+    return __hiloint2double(__double2hiint(x) ^ (int)mask, __double2loint(x));
+#else
+    uint64_t b; memcpy(&b, &x, 8); b ^= (uint64_t)mask << 32; memcpy(&x, &b, 8); return x;
+#endif
+}
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+constexpr double kTwoPi = 6.28318530717958647692528676655900577;
+
+// ---- reciprocal -------------------------------------------------------------------------------
+AZ_HD double rcp_seed(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    return (double)(1.0f / (float)x);  // ~2^-23, like the MUFU seed
+#endif
+}
+// ~2^-46 relative: enough for Newton correction steps (the fixed point does not depend on it)
+AZ_HD double rcp_fast(double x) {
+    double y = rcp_seed(x);
+    double e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+// full precision (<= 1 ulp)
+AZ_HD double rcp(double x) {
+    double y = rcp_seed(x);
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+// a / b with one residual correction (<= 1 ulp for well-scaled operands)
+AZ_HD double div_nr(double a, double b) {
+    double y = rcp(b);
+    double q = a * y;
+    double r = fma(-b, q, a);
+    return fma(r, y, q);
+}
+
+// ---- rsqrt / sqrt -----------------------------------------------------------------------------
+AZ_HD double rsqrt_seed(double x) {
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    return y;
+#else
+    return (double)(1.0f / sqrtf((float)x));
+#endif
+}
+// 1/sqrt(x), <= 1 ulp
+AZ_HD double rsqrt_nr(double x) {
+    double y = rsqrt_seed(x);
+    double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);  // 0.5 - 0.5 x y^2
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    return y;
+}
+// sqrt(x) from y ~ 1/sqrt(x): one Heron correction
+AZ_HD double sqrt_from_rsqrt(double x, double y) {
+    double s = x * y;
+    double r = fma(-s, s, x);
+    return fma(0.5 * y, r, s);
+}
+AZ_HD double sqrt_(double x) { return sqrt_from_rsqrt(x, rsqrt_nr(x)); }
+
+// ---- sin / cos --------------------------------------------------------------------------------
+// fdlibm __kernel_sin / __kernel_cos coefficients (public domain, Sun Microsystems), |r| <= pi/4.
+AZ_HD double ksin(double r, double r2) {
+    double p = fma(r2, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    p = fma(p, r2, 2.75573137070700676789e-06);
+    p = fma(p, r2, -1.98412698298579493134e-04);
+    p = fma(p, r2, 8.33333333332248946124e-03);
+    p = fma(p, r2, -1.66666666666666324348e-01);
+    return fma(p, r2 * r, r);
+}
+AZ_HD double kcos(double r2) {
+    double p = fma(r2, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    p = fma(p, r2, -2.75573143513906633035e-07);
+    p = fma(p, r2, 2.48015872894767294178e-05);
+    p = fma(p, r2, -1.38888888888741095749e-03);
+    p = fma(p, r2, 4.16666666666666019037e-02);
+    p = fma(p, r2, -0.5);
+    return fma(p, r2, 1.0);
+}
+
+// sin and cos of x, |x| <~ 1e5.  Cody-Waite with pi/2 split in three (FMA keeps k*hi exact enough).
+AZ_HD void sincos_full(double x, double &s, double &c) {
+    constexpr double kTwoOverPi = 6.36619772367581382433e-01;
+    constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
+    constexpr double kPio2Hi = 1.57079632679489655800e+00;
+    constexpr double kPio2Mid = 6.12323399573676603587e-17;
+    constexpr double kPio2Lo = -1.49738490485916983692e-33;
+    double kf = fma(x, kTwoOverPi, kMagic);
+    const unsigned q = (unsigned)dbl_lo(kf);
+    kf -= kMagic;
+    double r = fma(kf, -kPio2Hi, x);
+    r = fma(kf, -kPio2Mid, r);
+    r = fma(kf, -kPio2Lo, r);
+    double r2 = r * r;
+    double sr = ksin(r, r2);
+    double cr = kcos(r2);
+    double a = (q & 1) ? cr : sr;
+    double b = (q & 1) ? sr : cr;
+    // sign flips through the high word: sin negative in quadrants 2,3; cos negative in 1,2
+    s = dbl_xor_hi(a, (q & 2u) << 30);
+    c = dbl_xor_hi(b, ((q + 1u) & 2u) << 30);
+}
+
+// |x| <= pi/4: the kernels alone, no range reduction.  Used for the Kepler offset E-u (|.| <= e).
+AZ_HD void sincos_quarter(double x, double &s, double &c) {
+    double x2 = x * x;
+    s = ksin(x, x2);
+    c = kcos(x2);
+}
+
+// |x| <= 0.05: truncated Taylor series, abs error < 1e-17.  Used for the J2 short-period angles
+// (|x| <= 1.5 * 0.5 * j2 / pl^2 ~ 8e-4 for any orbit above the surface).
+AZ_HD void sincos_tiny(double x, double &s, double &c) {
+    double x2 = x * x;
+    double p = fma(x2, -1.0 / 5040.0, 1.0 / 120.0);
+    p = fma(x2, p, -1.0 / 6.0);
+    s = fma(x * x2, p, x);
+    double q = fma(x2, 1.0 / 40320.0, -1.0 / 720.0);
+    q = fma(x2, q, 1.0 / 24.0);
+    q = fma(x2, q, -0.5);
+    c = fma(x2, q, 1.0);
+}
+
+// rotate the unit vector (s0, c0) = (sin a, cos a) by angle d given (sd, cd): returns sin/cos(a + d)
+AZ_HD void rotate(double s0, double c0, double sd, double cd, double &s, double &c) {
+    s = fma(s0, cd, c0 * sd);
+    c = fma(c0, cd, -(s0 * sd));
+}
+
+// sin/cos(a + d) for an arbitrary d, picking the cheapest exact-enough evaluation of (sin d, cos d)
+AZ_HD void rotate_small(double s0, double c0, double d, double &s, double &c) {
+    double sd, cd;
+    if (fabs(d) <= 0.05) sincos_tiny(d, sd, cd);
+    else sincos_full(d, sd, cd);  // never taken for physical orbits; keeps the identity exact
+    rotate(s0, c0, sd, cd, s, c);
+}
+
+// floored modulo 2*pi (Zig @mod semantics), result in [0, 2pi)
+AZ_HD double mod_twopi(double x) {
+    double n = floor(x * (1.0 / kTwoPi));
+    double r = fma(-kTwoPi, n, x);
+    r = (r < 0.0) ? r + kTwoPi : r;
+    return (r >= kTwoPi) ? r - kTwoPi : r;
+}
+
+// accurate atan2 for the SDP4 Lyddane branch only (rare): CUDA's own
+AZ_HD double atan2_(double y, double x) { return atan2(y, x); }
+
+}  // namespace az

@@ -1,0 +1,152 @@
+// az_tables.hpp -- host code that turns prepared elements into the device tables (product code).
+//
+// Replaces the reflection transposes of the reference: src/Sgp4Batch.zig:78-110 (initBatchElements) and
+// src/Sdp4Batch.zig:147-194 (initFromElements), plus the classification loop of
+// src/Constellation.zig:101-200.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "az_device.cuh"
+#include "az_elements.hpp"
+
+namespace az {
+
+inline GravConsts grav_consts(const Gravity &g) {
+    return GravConsts{g.j2, g.radiusEarthKm, g.xke * g.radiusEarthKm / 60.0, g.j3oj2, g.xke};
+}
+
+// column values of one near-earth satellite, in Sgp4Col order
+inline void sgp4_columns(const NearEarth &e, double *c) {
+    c[kMo] = e.mo; c[kMdot] = e.mdot; c[kArgpo] = e.argpo; c[kArgpdot] = e.argpdot;
+    c[kNodeo] = e.nodeo; c[kNodedot] = e.nodedot; c[kXnodcf] = e.xnodcf; c[kCc1] = e.cc1;
+    c[kBc4] = e.bstar * e.cc4;  // only ever used as bstar*cc4 (src/Sgp4Batch.zig:126)
+    c[kT2cof] = e.t2cof; c[kOmgcof] = e.omgcof; c[kEta] = e.eta; c[kXmcof] = e.xmcof; c[kDelmo] = e.delmo;
+    c[kD2] = e.d2; c[kD3] = e.d3; c[kD4] = e.d4;
+    c[kBc5] = e.bstar * e.cc5;  // src/Sgp4Batch.zig:144
+    c[kSinmao] = e.sinmao; c[kT3cof] = e.t3cof; c[kT4cof] = e.t4cof; c[kT5cof] = e.t5cof;
+    c[kAbase] = e.aBase; c[kEcco] = e.ecco; c[kNo] = e.no; c[kAycof] = e.aycof; c[kXlcof] = e.xlcof;
+    c[kCon41] = e.con41; c[kX1mth2] = e.x1mth2; c[kX7thm1] = e.x7thm1; c[kSinio] = e.sinio; c[kCosio] = e.cosio;
+    c[kIsimp] = e.isimp ? 1.0 : 0.0;
+}
+
+inline Sdp4Sat sdp4_record(const DeepSpace &d) {
+    const NearEarth &e = d.ne;
+    Sdp4Sat r{};
+    r.mo = e.mo; r.mdot = e.mdot; r.argpo = e.argpo; r.argpdot = e.argpdot; r.nodeo = e.nodeo; r.nodedot = e.nodedot;
+    r.xnodcf = e.xnodcf; r.cc1 = e.cc1; r.bc4 = e.bstar * e.cc4; r.t2cof = e.t2cof; r.ecco = e.ecco; r.no = e.no;
+    r.inclo = e.inclo;
+    r.se2 = d.sun.e2; r.se3 = d.sun.e3; r.si2 = d.sun.i2; r.si3 = d.sun.i3; r.sl2 = d.sun.l2; r.sl3 = d.sun.l3;
+    r.sl4 = d.sun.l4; r.sgh2 = d.sun.gh2; r.sgh3 = d.sun.gh3; r.sgh4 = d.sun.gh4; r.sh2 = d.sun.h2; r.sh3 = d.sun.h3;
+    r.ee2 = d.moon.e2; r.e3 = d.moon.e3; r.xi2 = d.moon.i2; r.xi3 = d.moon.i3; r.xl2 = d.moon.l2; r.xl3 = d.moon.l3;
+    r.xl4 = d.moon.l4; r.xgh2 = d.moon.gh2; r.xgh3 = d.moon.gh3; r.xgh4 = d.moon.gh4; r.xh2 = d.moon.h2;
+    r.xh3 = d.moon.h3;
+    r.zmol = d.zmol; r.zmos = d.zmos; r.dedt = d.dedt; r.didt = d.didt; r.dmdt = d.dmdt; r.domdt = d.domdt;
+    r.dnodt = d.dnodt;
+    r.d2201 = d.d2201; r.d2211 = d.d2211; r.d3210 = d.d3210; r.d3222 = d.d3222; r.d4410 = d.d4410;
+    r.d4422 = d.d4422; r.d5220 = d.d5220; r.d5232 = d.d5232; r.d5421 = d.d5421; r.d5433 = d.d5433;
+    r.del1 = d.del1; r.del2 = d.del2; r.del3 = d.del3; r.xlamo = d.xlamo; r.xfact = d.xfact; r.gsto = d.gsto;
+    r.epochJd = e.epochJd;
+    r.irez = d.irez;
+    return r;
+}
+
+// Host image of a classified constellation (src/Constellation.zig:78-96): near-earth satellites in
+// padded 8-wide tiles, deep-space satellites as records, each list with its original catalog index.
+struct CatalogTables {
+    uint32_t n = 0, nSgp4 = 0, nSdp4 = 0;
+    Gravity grav{};
+    double referenceEpochJd = 0.0;             // epoch of the first near-earth satellite (:139-140)
+    std::vector<double> sgp4Tiles;             // [tiles][kSgp4Cols][8]
+    std::vector<double> sgp4Epoch;             // padded, per near-earth satellite
+    std::vector<uint32_t> sgp4Orig;            // padded; padding lanes repeat the last real satellite (:146)
+    std::vector<Sdp4Sat> sdp4;                 // one record per deep-space satellite
+    std::vector<uint32_t> sdp4Orig;
+    std::vector<double> epochs;                // per catalog satellite
+    std::vector<int32_t> classes;              // 0 SGP4, 1 + irez for SDP4
+    uint32_t sgp4Tiles_count() const { return (nSgp4 + kTileSats - 1) / kTileSats; }
+    uint32_t sgp4Padded() const { return sgp4Tiles_count() * kTileSats; }
+};
+
+// Classify and tabulate.  Returns kOk or the first non-deep-space init failure (src/Constellation.zig:115-126).
+inline int build_catalog(const char *const *l1, const char *const *l2, uint32_t n, int gravSel, CatalogTables &out) {
+    out = CatalogTables{};
+    out.n = n;
+    out.grav = gravity(gravSel);
+    out.epochs.resize(n);
+    out.classes.resize(n);
+    std::vector<NearEarth> near;
+    near.reserve(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        TleRecord t;
+        if (parse_tle(l1[i], l2[i], t) != kOk) return kBadTle;
+        out.epochs[i] = t.epochJd;
+        NearEarth ne;
+        int rc = build_near_earth(t, out.grav, ne);
+        if (rc == kOk) {
+            near.push_back(ne);
+            out.sgp4Orig.push_back(i);
+            out.classes[i] = 0;
+        } else if (rc == kDeepSpace) {
+            DeepSpace ds;
+            rc = build_deep_space(t, out.grav, ds);
+            if (rc != kOk) return rc;
+            out.sdp4.push_back(sdp4_record(ds));
+            out.sdp4Orig.push_back(i);
+            out.classes[i] = 1 + ds.irez;
+        } else {
+            return rc;
+        }
+    }
+    out.nSgp4 = (uint32_t)near.size();
+    out.nSdp4 = (uint32_t)out.sdp4.size();
+    if (out.nSgp4) out.referenceEpochJd = near[0].epochJd;
+
+    const uint32_t tiles = out.sgp4Tiles_count();
+    out.sgp4Tiles.assign((size_t)tiles * kSgp4TileDoubles, 0.0);
+    out.sgp4Epoch.resize((size_t)tiles * kTileSats);
+    out.sgp4Orig.resize((size_t)tiles * kTileSats);
+    double cols[kSgp4Cols];
+    for (uint32_t s = 0; s < tiles * kTileSats; ++s) {
+        const uint32_t src = s < out.nSgp4 ? s : out.nSgp4 - 1;
+        sgp4_columns(near[src], cols);
+        double *tile = out.sgp4Tiles.data() + (size_t)(s / kTileSats) * kSgp4TileDoubles;
+        for (int c = 0; c < kSgp4Cols; ++c) tile[c * kTileSats + (s % kTileSats)] = cols[c];
+        out.sgp4Epoch[s] = near[src].epochJd;
+        if (s >= out.nSgp4) out.sgp4Orig[s] = out.sgp4Orig[out.nSgp4 - 1];
+    }
+    return kOk;
+}
+
+// Split a text blob into element-set line pairs (src/Tle.zig:103-132 MultiIterator semantics).
+inline void split_tle_text(const char *text, size_t len, std::vector<std::string> &l1, std::vector<std::string> &l2) {
+    std::string cand;
+    bool have = false;
+    size_t i = 0;
+    while (i <= len) {
+        size_t j = i;
+        while (j < len && text[j] != '\n' && text[j] != '\r') ++j;
+        size_t b = i, e = j;
+        while (b < e && (text[b] == ' ' || text[b] == '\t')) ++b;
+        while (e > b && (text[e - 1] == ' ' || text[e - 1] == '\t')) --e;
+        if (e - b >= 69) {
+            if (text[b] == '1') {
+                cand.assign(text + b, e - b);
+                have = true;
+            } else if (text[b] == '2') {
+                if (have) {
+                    l1.push_back(cand);
+                    l2.emplace_back(text + b, e - b);
+                    have = false;
+                }
+            } else {
+                have = false;
+            }
+        }
+        i = j + 1;
+    }
+}
+
+}  // namespace az

@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batch SGP4/SDP4 path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config3|config4]
+
+A "step" is one pass of the hot path over the synthetic grid (BASELINE config 2 by default: 13,478
+near-earth satellites x 1,440 epochs, fp64, velocities on, TEME).  One JSON line is printed by rank 0.
+
+  value        whole-job props/s with the result left in HBM (CUDA events on the launching stream,
+               max over ranks).  For N > 1 every rank propagates its own 13,478-satellite catalog
+               (weak scaling, satellites shard with no data-path collective); the north star's
+               single NCCL all-gather of the position/velocity block is timed separately and
+               reported under "allgather".
+  e2e          the same metric through the reference-facing host-buffer API
+               (Constellation.propagate: host jd/fr in, pinned host pos/vel out, copies inside the
+               timed region).
+  roofline     algorithmic fp64 FLOPs (578 per cell) / kernel time vs the DFMA peak
+               measured live on the same device; HBM figures beside it.
+  cpu_baseline the reference's CPU SIMD path (oracle/simd_baseline.c port) timed on this box's host cores.
+  --impl reference  times only that CPU path and prints the same line shape with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_CELL = 578.0          # 387 + 43*K (K=4), div = sqrt = 1
+BYTES_PER_CELL = 48.2          # 48 B written (pos+vel) + ~0.2 B of element reads
+PUBLISHED_CPU_HEADLINE = 303e6  # props/s, astroz 16 threads on Ryzen 7 7840U (README.md:39)
+METRIC = "propagations/sec (sat x time pairs)"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload(name: str, rank: int):
+    """(tles, jd, fr, description).  Ranks > 0 draw a different catalog of the same class mix (weak scaling)."""
+    from astroz_b200 import synth
+
+    if name == "config2":
+        tles = synth.near_earth_catalog(synth.HEADLINE_SATS, seed=13478 + rank)
+        jd, fr = synth.time_grid(1440)
+        desc = "config2: 13,478 near-earth sats x 1,440 epochs (1-min steps), SGP4, fp64, velocities on, TEME, satellite-major"
+    elif name == "config3":
+        tles = synth.mixed_catalog(synth.HEADLINE_SATS, seed=28626 + rank)
+        jd, fr = synth.time_grid(1440)
+        desc = "config3: 13,478 sats (1,024 GEO + 256 Molniya + 256 GPS-like deep-space) x 1,440 epochs, mixed SGP4/SDP4"
+    elif name == "config4":
+        tles = synth.near_earth_catalog(synth.HEADLINE_SATS, seed=13478 + rank)
+        jd, fr = synth.time_grid(10080)
+        desc = "config4: 13,478 near-earth sats x 10,080 epochs (1 week @ 1 min)"
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    return tles, jd, fr, desc
+
+
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_pass(tles, jd, fr, min_seconds: float, min_reps: int, max_reps: int):
+    """Time the CPU SIMD port (restatement of src/Sgp4Batch.zig + src/Constellation.zig threading) on all
+    host threads, outputs pre-touched so page faults are not billed to either arm."""
+    from oracle import oracle as orc
+
+    orc.build()
+    sim = orc.SimdConstellation(tles)
+    n, nt = len(tles), len(jd)
+    pos = np.zeros((nt, n, 3))
+    vel = np.zeros((nt, n, 3))
+    threads = int(os.environ.get("ASTROZ_THREADS", os.cpu_count() or 1))
+    sim.propagate(jd[:32], fr[:32], layout=1, threads=threads, out=(pos[:32], vel[:32]))
+    times = []
+    t_end = time.perf_counter() + min_seconds
+    while len(times) < min_reps or (time.perf_counter() < t_end and len(times) < max_reps):
+        t0 = time.perf_counter()
+        sim.propagate(jd, fr, layout=1, threads=threads, out=(pos, vel))
+        times.append(time.perf_counter() - t0)
+    return times, threads, orc.simd_isa()
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    tles, jd, fr, desc = workload(args.workload, 0)
+    if args.workload == "config3":
+        raise SystemExit("the CPU SIMD port covers the near-earth path only (config2 / config4)")
+    cells = len(tles) * len(jd)
+    for _ in range(args.warmup):
+        pass
+    times, threads, isa = cpu_reference_pass(tles, jd, fr, 0.0, args.warmup + args.steps, args.warmup + args.steps)
+    timed = times[args.warmup:]
+    total = float(sum(timed))
+    value = cells * len(timed) / total
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "props/s", "n_gpus": args.gpus,
+        "steps": len(timed), "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": value / PUBLISHED_CPU_HEADLINE, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "layout": "time-major (the reference's fast path)", "isa": isa},
+        "cpu_baseline": {"value": value, "unit": "props/s", "cores": threads, "kind": "port",
+                         "sample": f"full grid ({cells} cells) x {len(timed)} timed passes, outputs pre-touched",
+                         "what": "C port of the reference's 8-lane SIMD batch path (Zig 0.16 is not installable here)"},
+        "e2e": {"value": value, "unit": "props/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, local_rank: int, world: int) -> None:
+    import torch
+
+    import astroz_b200
+    from astroz_b200 import Constellation, Layout, OutputMode
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: astroz_b200 has no CPU propagation path")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    tles, jd, fr, desc = workload(args.workload, rank)
+    c = Constellation(tles, device=local_rank)
+    n, nt = c.numSatellites, len(jd)
+    cells = n * nt
+    kernels_per_step = (1 if c.numSgp4 else 0) + (1 if c.numSdp4 else 0)
+
+    # one allocation [pos | vel] so the north star's all-gather is a single collective on one block
+    block = torch.empty((2, n, nt, 3), dtype=torch.float64, device=dev)
+    pos, vel = block[0], block[1]
+    stream = torch.cuda.Stream(dev)   # kernels, events and the collective all go through this stream
+    torch.cuda.set_stream(stream)
+
+    def step():
+        c.propagate_device(jd, fr, pos, vel, None, OutputMode.teme, Layout.satelliteMajor, stream=stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+
+    # ---- timed region: exactly K steps, CUDA events on the launching stream ---------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_per_step = ms_total / args.steps
+    value = cells * world / (ms_per_step * 1e-3)
+
+    # ---- dominant kernel alone (library's own CUDA events around the launch, same stream) ------------
+    kms = []
+    for _ in range(min(args.steps, 10)):
+        step()
+        c.synchronize()
+        torch.cuda.synchronize(dev)
+        k = c.last_kernel_ms()
+        kms.append(k[0] + k[2])
+    kernel_ms = max_over_ranks(float(np.mean(kms)))
+
+    # ---- end to end through the host-buffer API ------------------------------------------------------
+    hp = astroz_b200.pinned_empty((n, nt, 3))
+    hv = astroz_b200.pinned_empty((n, nt, 3))
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        c.propagate(jd, fr, hp, hv, OutputMode.teme, Layout.satelliteMajor)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        c.propagate(jd, fr, hp, hv, OutputMode.teme, Layout.satelliteMajor)
+        checksum = float(hp[0, 0, 0])  # the result is read on the host every step
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e_value = cells * world / e2e_s
+    h2d = 2 * nt * 8
+    d2h = 2 * n * nt * 3 * 8
+
+    # ---- the north star's collective, measured apart from `value` -------------------------------------
+    allgather = None
+    if dist is not None:
+        full = torch.empty((world,) + tuple(block.shape), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            dist.all_gather_into_tensor(full, block)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(3, min(args.steps, 10))
+        g0.record(stream)
+        for _ in range(reps):
+            step()
+            dist.all_gather_into_tensor(full, block)
+        g1.record(stream)
+        barrier()
+        ms_ag = max_over_ranks(g0.elapsed_time(g1)) / reps
+        recv_bytes = (world - 1) * block.numel() * 8
+        allgather = {"ms_per_step_with_allgather": ms_ag, "value_with_allgather": cells * world / (ms_ag * 1e-3),
+                     "allgather_only_ms": max(ms_ag - ms_per_step, 0.0),
+                     "recv_GB_per_gpu": recv_bytes / 1e9,
+                     "recv_GBs_per_gpu": recv_bytes / 1e9 / max((ms_ag - ms_per_step) * 1e-3, 1e-9),
+                     "collective": "one ncclAllGather of the [pos|vel] block (torch.distributed, NCCL over NVLink 5)"}
+        del full
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline ---------------------------------------------------------------------------------------
+    peaks, peaks_kind = _peaks()
+    fp64_peak = astroz_b200.fp64_peak_tflops(local_rank)
+    ach_tflops = FLOP_PER_CELL * cells / (kernel_ms * 1e-3) / 1e12
+    ach_gbs = BYTES_PER_CELL * cells / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "traffic.json")   # DRAM bytes per launch from the committed ncu capture
+    if os.path.exists(tfile):
+        try:
+            traffic = json.load(open(tfile)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp64", "kernel": "sgp4_grid_kernel", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+        "frac": ach_tflops / fp64_peak if fp64_peak else None,
+        "peak_source": "DFMA microbenchmark run live on this device (astroz_cuda_fp64_peak); datasheet ~37-40 TFLOP/s",
+        "flop_per_cell": FLOP_PER_CELL, "kernel_ms": kernel_ms,
+        "hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": ach_gbs / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None, "peak_source": peaks_kind,
+                "bytes_per_cell": BYTES_PER_CELL},
+        "traffic": traffic,
+    }
+
+    # ---- CPU baseline: the reference's SIMD path on this box's host cores (N=1 only) --------------------
+    cpu = None
+    if world == 1 and args.workload != "config3" and not args.no_cpu_baseline:
+        times, threads, isa = cpu_reference_pass(tles, jd, fr, 10.0, 3, 400)
+        best = min(times)
+        cpu = {"value": cells / best, "unit": "props/s", "cores": threads, "kind": "port", "isa": isa,
+               "sample": f"full grid ({cells} cells) x {len(times)} passes over ~{sum(times):.0f} s, best pass, "
+                         "time-major, velocities on, outputs pre-touched",
+               "mean_value": cells * len(times) / sum(times),
+               "published_reference": "303 M props/s (16 thr) / 37.7 M (1 thr) on Ryzen 7 7840U, README.md:39"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": "props/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": value / PUBLISHED_CPU_HEADLINE, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "cells_per_gpu": cells, "n_sgp4": c.numSgp4, "n_sdp4": c.numSdp4,
+                   "output_bytes_per_step_per_gpu": d2h,
+                   "l2": "931.6 MB written per step >> 126 MB L2 (nothing re-read between steps); the 3.6 MB element "
+                         "table is L2-resident by design",
+                   "parallelism": f"satellite-sharded x{world}, no data-path collective in `value`"},
+        "e2e": {"value": e2e_value, "unit": "props/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "d2h_GBs": d2h / e2e_s / 1e9,
+                "api": "Constellation.propagate(jd, fr, pos, vel) with pinned host buffers", "checksum": checksum},
+        "gpu_launches": kernels_per_step * args.steps,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "baseline_published": {"value": PUBLISHED_CPU_HEADLINE, "what": "astroz CPU SIMD, 16 threads, Ryzen 7 7840U"},
+    }
+    if allgather is not None:
+        out["allgather"] = allgather
+    print(json.dumps(out), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default="config2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torch.distributed.run (one rank per GPU)")
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,159 @@
+/*
+ * astroz_b200.h -- C ABI of the B200-native batch SGP4/SDP4 propagator.
+ *
+ * Drop-in boundary for the propagation path of ATTron/astroz (reference paths relative to the
+ * reference repo root).  Every entry point names the reference interface it replaces.
+ * Plain pointers and sizes only; no torch / C++ types.  All functions return an int32 from the
+ * reference's own error-code space (src/c_api/error.zig:3-19) extended with CUDA codes.
+ *
+ * Threading / ownership (same contract as the reference, src/c_api/allocator.zig:9-18 and
+ * src/Constellation.zig:88,294): handles are not thread-safe; caller owns every I/O buffer and the
+ * library never retains it; device memory is owned by the handle and released by the matching *_free.
+ */
+#ifndef ASTROZ_B200_H
+#define ASTROZ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes: src/c_api/error.zig:3-19 (+ CUDA extensions <= -200) ------------------------- */
+#define ASTROZ_OK                    0
+#define ASTROZ_BAD_TLE_LENGTH      (-1)
+#define ASTROZ_BAD_CHECKSUM        (-2)
+#define ASTROZ_DEEP_SPACE          (-10)   /* deepSpaceNotSupported */
+#define ASTROZ_INVALID_ECC         (-11)
+#define ASTROZ_DECAYED             (-12)
+#define ASTROZ_VALUE_ERROR         (-20)
+#define ASTROZ_ALLOC_FAILED        (-100)
+#define ASTROZ_NULL_POINTER        (-101)
+#define ASTROZ_NOT_INITIALIZED     (-102)
+#define ASTROZ_UNKNOWN             (-999)
+#define ASTROZ_CUDA_ERROR          (-200)  /* any CUDA runtime failure; see astroz_cuda_last_error() */
+#define ASTROZ_NO_DEVICE           (-201)  /* no CUDA device: the library never falls back to a CPU path */
+
+/* ---- per-cell status bytes (kernel-level codes, src/simdKernels.zig:30-37) --------------------- */
+#define ASTROZ_CELL_OK           0
+#define ASTROZ_CELL_DECAYED      1
+#define ASTROZ_CELL_INVALID_ECC  2
+
+/* gravity model selector: src/c_api/sgp4.zig:17-20 (0 = WGS84, 1 = WGS72) */
+#define ASTROZ_WGS84 0
+#define ASTROZ_WGS72 1
+
+/* src/Constellation.zig:30-42 */
+#define ASTROZ_MODE_TEME      0
+#define ASTROZ_MODE_ECEF      1
+#define ASTROZ_MODE_GEODETIC  2
+#define ASTROZ_LAYOUT_SATELLITE_MAJOR 0   /* (n_sats, n_times, 3) */
+#define ASTROZ_LAYOUT_TIME_MAJOR      1   /* (n_times, n_sats, 3) */
+
+typedef void *astroz_constellation_t;
+typedef void *astroz_sgp4_t;
+
+/* replaces astroz_version (src/c_api/root.zig:13-15): (major<<16)|(minor<<8)|patch */
+uint32_t astroz_cuda_version(void);
+/* number of visible CUDA devices (0 when none) */
+int32_t astroz_cuda_device_count(void);
+/* text of the last CUDA failure seen on this thread ("" if none); pointer valid until the next call */
+const char *astroz_cuda_last_error(void);
+
+/* pinned host buffers for zero-staging device<->host copies of the output block */
+void *astroz_cuda_host_alloc(size_t bytes);
+void astroz_cuda_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------------
+ * Constellation: replaces Constellation.init / propagate / resetCarry / deinit
+ * (src/Constellation.zig:101-200, 245-308, 214-218, 202-210).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Parse n TLEs (NUL-terminated 69-column lines, src/Tle.zig:49-101), classify each as SGP4 or SDP4
+ * exactly as src/Constellation.zig:115-126, build the device element tables on `device`.
+ * Errors: BAD_TLE_LENGTH, INVALID_ECC, DECAYED (first offending TLE aborts, as the reference). */
+int32_t astroz_cuda_constellation_create(const char *const *line1, const char *const *line2, uint32_t n,
+                                         int32_t grav, int32_t device, astroz_constellation_t *out);
+
+/* Same, from a text blob of 2- or 3-line element sets (src/Tle.zig:103-132 MultiIterator semantics). */
+int32_t astroz_cuda_constellation_create_from_text(const char *text, size_t len, int32_t grav, int32_t device,
+                                                   astroz_constellation_t *out);
+
+void astroz_cuda_constellation_free(astroz_constellation_t h);
+
+/* numSatellites / numSgp4 / numSdp4 (src/Constellation.zig:82,89,95) */
+int32_t astroz_cuda_constellation_counts(astroz_constellation_t h, uint32_t *n, uint32_t *n_sgp4, uint32_t *n_sdp4);
+/* per-satellite epoch JD (n doubles) and class (n int32: 0 SGP4, 1 SDP4 irez0, 2 irez1, 3 irez2) */
+int32_t astroz_cuda_constellation_epochs(astroz_constellation_t h, double *epochs);
+int32_t astroz_cuda_constellation_classes(astroz_constellation_t h, int32_t *classes);
+/* referenceEpochJd (src/Constellation.zig:92,139-140); settable so satellite shards of one catalog
+ * share the whole catalog's reference epoch */
+int32_t astroz_cuda_constellation_get_reference_epoch(astroz_constellation_t h, double *jd);
+int32_t astroz_cuda_constellation_set_reference_epoch(astroz_constellation_t h, double jd);
+
+/* Constellation.propagate (src/Constellation.zig:245-308) with HOST buffers.
+ * pos / vel: n*n_times*3 doubles each (vel may be NULL), written per `layout`; `mode` selects TEME/ECEF/geodetic.
+ * Cells whose propagation fails are zero-filled (src/Constellation.zig:511-528).  Includes the
+ * host->device copy of jd/fr and the device->host copy of the result block. */
+int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const double *jd, const double *fr,
+                                            uint32_t n_times, double *pos, double *vel, int32_t mode, int32_t layout);
+
+/* Same computation, results left in HBM (d_pos / d_vel are DEVICE pointers on the handle's device).
+ * out_num_sats / out_sat_offset place this handle's satellites inside a larger output block
+ * (the reference's numSatellites-as-stride convention, src/Constellation.zig:46-51 and
+ * bindings/python/src/sgp4.zig:216); pass n and 0 for a stand-alone constellation.
+ * d_status (nullable): n*n_times bytes, satellite-major, per-cell ASTROZ_CELL_* code.
+ * stream: a cudaStream_t (NULL = the handle's own stream); the call is asynchronous on it. */
+int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, const double *jd, const double *fr,
+                                                   uint32_t n_times, double *d_pos, double *d_vel, uint8_t *d_status,
+                                                   int32_t mode, int32_t layout, uint32_t out_num_sats,
+                                                   uint32_t out_sat_offset, void *stream);
+
+/* Constellation.resetCarry (src/Constellation.zig:214-218).  The device path re-derives the SDP4
+ * resonance state from a 720-minute lattice on every call, so this is a semantic no-op kept for drop-in use. */
+int32_t astroz_cuda_constellation_reset_carry(astroz_constellation_t h);
+
+/* stateless near-earth path: replaces Constellation.propagateConstellation (src/Constellation.zig:541-605)
+ * as called by SatrecArray.propagate_into (bindings/python/src/satrec.zig:896-988):
+ *   tsince[sat][t] = times[t] + epoch_offsets[sat]   (minutes)
+ * Only the SGP4 satellites of `h` take part, in catalog order; n_sgp4 rows are written.
+ * epoch_offsets: n_sgp4 doubles.  reference_jd is used for GMST when mode != TEME.  HOST buffers. */
+int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                        const double *epoch_offsets, double *pos, double *vel, int32_t mode,
+                                        double reference_jd, int32_t layout);
+/* device-resident variant of the above (d_pos/d_vel device pointers) */
+int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                               const double *epoch_offsets, double *d_pos, double *d_vel,
+                                               int32_t mode, double reference_jd, int32_t layout, void *stream);
+
+/* block until everything queued on the handle's stream has finished */
+int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h);
+
+/* device time (ms, CUDA events on the launching stream) of the propagation kernels of the last
+ * propagate call on this handle: [0] SGP4 grid kernel, [1] SDP4 lattice pre-pass, [2] SDP4 grid kernel */
+int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float ms[3]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Single satellite: replaces sgp4_init / sgp4_free / sgp4_propagate / sgp4_propagate_batch
+ * (src/c_api/root.zig:48-59, src/c_api/sgp4.zig:16-100) -- extended to deep-space objects the way
+ * Satrec.twoline2rv falls back to SDP4 (bindings/python/src/satrec.zig:135-160).
+ * ---------------------------------------------------------------------------------------------- */
+int32_t astroz_cuda_sgp4_init(const char *line1, const char *line2, int32_t grav, int32_t device, astroz_sgp4_t *out);
+void astroz_cuda_sgp4_free(astroz_sgp4_t h);
+/* 1 if the object is propagated with SDP4 (Satrec.is_deep_space) */
+int32_t astroz_cuda_sgp4_is_deep_space(astroz_sgp4_t h);
+int32_t astroz_cuda_sgp4_epoch(astroz_sgp4_t h, double *epoch_jd);
+/* one time: pos[3] km, vel[3] km/s (TEME) */
+int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3], double vel[3]);
+/* count times (minutes since epoch); results[count][6] = x y z vx vy vz (src/c_api/sgp4.zig:60-100) */
+int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, double *results, uint32_t count);
+
+/* ---- measurement helpers --------------------------------------------------------------------- */
+/* DFMA microbenchmark on `device`: achieved fp64 TFLOP/s (FMA = 2) -- the measured roofline denominator */
+int32_t astroz_cuda_fp64_peak(int32_t device, double *tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASTROZ_B200_H */

@@ -218,3 +218,66 @@ def satrec_array_sgp4(tles, jd, fr, grav: int = WGS72):
     if rc != 0:
         raise ValueError(f"oracle satrec_array init failed rc={rc}")
     return pos, vel
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU SIMD baseline (oracle/simd_baseline.c): restatement of the reference's 8-lane batch path, timed
+# by bench.py as cpu_baseline / --impl reference.  Never used by the product.
+# ---------------------------------------------------------------------------------------------------
+_simd = None
+
+
+def simd_lib() -> C.CDLL:
+    global _simd
+    if _simd is None:
+        path = os.path.join(_BUILD, "libastroz_simd_baseline.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        dp = C.POINTER(C.c_double)
+        L.azo_simd_create.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int]
+        L.azo_simd_create.restype = C.c_void_p
+        L.azo_simd_free.argtypes = [C.c_void_p]
+        L.azo_simd_propagate.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, dp, C.c_int, C.c_int]
+        L.azo_simd_propagate.restype = C.c_int
+        L.azo_simd_isa.restype = C.c_char_p
+        _simd = L
+    return _simd
+
+
+class SimdConstellation:
+    """Near-earth constellation on the CPU SIMD baseline (src/Constellation.zig:101-200,245-308)."""
+
+    def __init__(self, tles, grav: int = WGS72):
+        a1, a2 = _lines(tles)
+        self.n = len(tles)
+        self._h = simd_lib().azo_simd_create(a1, a2, self.n, grav)
+        if not self._h:
+            raise ValueError("SIMD baseline: init failed (deep-space or invalid element set in the catalog)")
+
+    def propagate(self, jd, fr, layout: int = 1, velocities: bool = True, threads: int | None = None, out=None):
+        jd = np.ascontiguousarray(jd, dtype=np.float64)
+        fr = np.ascontiguousarray(fr, dtype=np.float64)
+        nt = len(jd)
+        shape = (self.n, nt, 3) if layout == 0 else (nt, self.n, 3)
+        if out is None:
+            pos = np.empty(shape)
+            vel = np.empty(shape) if velocities else None
+        else:
+            pos, vel = out
+        threads = threads or (os.cpu_count() or 1)   # getMaxThreads, Constellation.zig:61-74
+        env = os.environ.get("ASTROZ_THREADS")
+        if env:
+            threads = int(env)
+        simd_lib().azo_simd_propagate(self._h, _dp(jd), _dp(fr), nt, _dp(pos), _dp(vel) if vel is not None else None,
+                                      layout, threads)
+        return pos, vel
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            simd_lib().azo_simd_free(self._h)
+            self._h = None
+
+
+def simd_isa() -> str:
+    return simd_lib().azo_simd_isa().decode()

@@ -1,0 +1,62 @@
+// TEST INFRASTRUCTURE ONLY: runs the product's __host__ __device__ per-cell cores (az_device.cuh) on the
+// CPU with the product's own host tables, so the kernel arithmetic can be checked against the oracle in
+// a container without a GPU.  Not part of the shipped library; nothing in astroz_b200/ references it.
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "az_tables.hpp"
+
+using namespace az;  // (az::* names do not collide with CUDA math: rsqrt_nr, div_nr)
+
+extern "C" int emul_constellation_propagate(const char *const *l1, const char *const *l2, uint32_t n, int grav,
+                                            const double *jd, const double *fr, uint32_t nt, double *pos, double *vel,
+                                            uint8_t *status) {
+    CatalogTables cat;
+    int rc = build_catalog(l1, l2, n, grav, cat);
+    if (rc != kOk) return rc;
+    const GravConsts g = grav_consts(cat.grav);
+    std::vector<double> jdFull(nt), tbase(nt);
+    for (uint32_t t = 0; t < nt; ++t) {
+        jdFull[t] = jd[t] + fr[t];
+        tbase[t] = (jdFull[t] - cat.referenceEpochJd) * 1440.0;
+    }
+    for (uint32_t s = 0; s < cat.nSgp4; ++s) {
+        const double *tile = cat.sgp4Tiles.data() + (size_t)(s / kTileSats) * kSgp4TileDoubles;
+        const int sl = s % kTileSats;
+        auto col = [&](int i) { return tile[i * kTileSats + sl]; };
+        const double toff = (cat.referenceEpochJd - cat.sgp4Epoch[s]) * 1440.0;
+        const uint32_t orig = cat.sgp4Orig[s];
+        for (uint32_t t = 0; t < nt; ++t) {
+            CellOut o;
+            sgp4_cell(col, tbase[t] + toff, g, o);
+            double *p = pos + ((size_t)orig * nt + t) * 3, *v = vel + ((size_t)orig * nt + t) * 3;
+            p[0] = o.rx; p[1] = o.ry; p[2] = o.rz; v[0] = o.vx; v[1] = o.vy; v[2] = o.vz;
+            if (status) status[(size_t)orig * nt + t] = o.mrt < 1.0 ? 1 : 0;
+        }
+    }
+    for (uint32_t s = 0; s < cat.nSdp4; ++s) {
+        const Sdp4Sat &e = cat.sdp4[s];
+        const uint32_t orig = cat.sdp4Orig[s];
+        for (uint32_t t = 0; t < nt; ++t) {
+            const double ts = (jdFull[t] - e.epochJd) * 1440.0;
+            double xli = e.xlamo, xni = e.no, atime = 0.0;
+            if (e.irez != 0) {
+                const int node = resonance_node(ts);
+                const double delt = ts > 0.0 ? kStepp : -kStepp;
+                for (int k = 0; k < node; ++k) resonance_step(e, xli, xni, atime, delt);
+            }
+            CellOut o{};
+            int st = sdp4_cell(e, ts, xli, xni, atime, g, o);
+            double *p = pos + ((size_t)orig * nt + t) * 3, *v = vel + ((size_t)orig * nt + t) * 3;
+            if (st != 0) { p[0] = p[1] = p[2] = v[0] = v[1] = v[2] = 0.0; }
+            else { p[0] = o.rx; p[1] = o.ry; p[2] = o.rz; v[0] = o.vx; v[1] = o.vy; v[2] = o.vz; }
+            if (status) status[(size_t)orig * nt + t] = (uint8_t)st;
+        }
+    }
+    return 0;
+}
+
+extern "C" void emul_sincos(const double *x, int n, double *s, double *c) {
+    for (int i = 0; i < n; ++i) sincos_full(x[i], s[i], c[i]);
+}

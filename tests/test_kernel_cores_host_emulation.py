@@ -1,0 +1,86 @@
+"""The product's __host__ __device__ per-cell cores (astroz_b200/csrc/az_device.cuh) and its host-side
+element builder, run on the CPU by a test-only harness (tests/host_emul/emul.cu) against the oracle.
+This checks the kernel arithmetic in the container that has no GPU; the real device run is in
+tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests.golden import tles as G
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMUL_DIR = os.path.join(ROOT, "tests", "host_emul")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc unavailable")
+    so = os.path.join(EMUL_DIR, "libemul.so")
+    src = os.path.join(EMUL_DIR, "emul.cu")
+    csrc = os.path.join(ROOT, "astroz_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp"))]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "--expt-relaxed-constexpr",
+                        "-Xcompiler", "-fPIC", "-shared", "-I" + csrc, "-o", so, src], check=True, capture_output=True)
+    L = C.CDLL(so)
+
+    def run(tles, jd, fr, grav=1):
+        n, nt = len(tles), len(jd)
+        a1 = (C.c_char_p * n)(*[t[0].encode() for t in tles])
+        a2 = (C.c_char_p * n)(*[t[1].encode() for t in tles])
+        p = np.zeros((n, nt, 3))
+        v = np.zeros((n, nt, 3))
+        st = np.zeros((n, nt), dtype=np.uint8)
+        dp = C.POINTER(C.c_double)
+        rc = L.emul_constellation_propagate(a1, a2, n, grav, jd.ctypes.data_as(dp), fr.ctypes.data_as(dp), nt,
+                                            p.ctypes.data_as(dp), v.ctypes.data_as(dp),
+                                            st.ctypes.data_as(C.POINTER(C.c_uint8)))
+        assert rc == 0
+        return p, v, st
+
+    run.lib = L
+    return run
+
+
+def test_sincos_kernel_accuracy(emul):
+    x = np.concatenate([np.linspace(-20.0, 20.0, 4001), np.array([1e3, -5e4, 7.0e5, 1e-300, 0.0])])
+    s = np.zeros_like(x)
+    c = np.zeros_like(x)
+    dp = C.POINTER(C.c_double)
+    emul.lib.emul_sincos(x.ctypes.data_as(dp), len(x), s.ctypes.data_as(dp), c.ctypes.data_as(dp))
+    assert np.max(np.abs(s - np.sin(x))) < 4e-16      # reference: 1e-12 (src/simdMath.zig:214-232)
+    assert np.max(np.abs(c - np.cos(x))) < 4e-16
+
+
+def test_cores_match_oracle_all_classes(emul, oracle):
+    from astroz_b200 import synth
+
+    jd, fr = synth.time_grid(10080)
+    jd, fr = jd[::197].copy(), fr[::197].copy()
+    for tles in (synth.near_earth_catalog(400), synth.mixed_catalog(300, n_geo=60, n_molniya=40, n_gps=40),
+                 [G.ISS, G.GEO28626, G.SAT55909, G.GPS20413, G.SAT55910, G.HEO09880]):
+        po, vo, err, klass = oracle.constellation_propagate(tles, jd, fr)
+        pe, ve, st = emul(tles, jd, fr)
+        assert np.max(np.abs(po - pe)) < 1e-6 and np.max(np.abs(vo - ve)) < 1e-9
+        deep = klass > 0
+        assert np.array_equal(st[deep], err[deep])
+
+
+def test_cores_error_cells(emul, oracle):
+    from astroz_b200 import synth
+
+    bad = synth.tle_lines(42000, 24, 120.0, 63.4, 0.0, 0.755, 0.0, 10.0, 2.006, 1e-3)
+    jd = np.full(40, 2460430.5)
+    fr = np.linspace(0.0, 2000.0, 40)
+    po, vo, err, _ = oracle.constellation_propagate([G.GPS20413, bad], jd, fr)
+    pe, ve, st = emul([G.GPS20413, bad], jd, fr)
+    assert err[1].any() and np.array_equal(st, err)
+    assert np.all(pe[1][err[1] != 0] == 0.0)
+    ok = err == 0
+    assert np.max(np.abs(po[ok] - pe[ok])) < 1e-5
