@@ -329,7 +329,7 @@ def test_headline_grid_properties(az, oracle, synth):
     rmag = torch.linalg.norm(pos, dim=2)
     vmag = torch.linalg.norm(vel, dim=2)
     assert torch.isfinite(pos).all() and torch.isfinite(vel).all()
-    assert float(rmag.min()) > 6378.0 + 100.0 and float(rmag.max()) < 6378.0 + 12000.0
+    assert float(rmag.min()) > 6378.0 + 60.0 and float(rmag.max()) < 6378.0 + 12000.0   # low-perigee shell decays to ~95 km
     assert float(vmag.min()) > 3.0 and float(vmag.max()) < 9.5
     rows = np.random.default_rng(7).choice(n, 160, replace=False)
     sub = [tles[i] for i in rows]
