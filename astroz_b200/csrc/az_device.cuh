@@ -54,26 +54,26 @@ AZ_HD void kepler_posvel(double am, double em, double mm, double argpm, double n
     const double aynl = fma(em, sa, temp * aycof);
     const double u = mm + argpm + temp * xlcof * axnl;  // xl - nodem, src/Sgp4.zig:680-682
 
-    double s0, c0;
-    sincos_full(u, s0, c0);
-    double s = s0, c = c0, eps = 0.0;
+    double s, c;
+    sincos_full(u, s, c);
+    double eps = 0.0;
 #pragma unroll 1
     for (int it = 0; it < 10; ++it) {  // src/Sgp4.zig:687-694
         const double esine = fma(axnl, s, -(aynl * c));
         const double ecose = fma(axnl, c, aynl * s);
         double delta = (esine - eps) * rcp_fast(1.0 - ecose);
-        if (fabs(delta) < 1.0e-12) {  // converged: apply the last step to first order and stop
-            const double s1 = fma(c, delta, s);
-            c = fma(-s, delta, c);
-            s = s1;
-            break;
-        }
-        delta = fmin(fmax(delta, -0.95), 0.95);
+        delta = fmin(fmax(delta, -AZK(clamp)), AZK(clamp));
         eps += delta;
-        double se, ce;
-        if (fabs(eps) <= 0.78) sincos_quarter(eps, se, ce);
-        else sincos_full(eps, se, ce);
-        rotate(s0, c0, se, ce, s, c);
+        // rotate (sin E, cos E) by the Newton step; a step below 0.05 rad uses the 9-op series
+        double sd, cd;
+        if (fabs(delta) <= AZK(tinyLimit)) sincos_tiny(delta, sd, cd);
+        else sincos_full(delta, sd, cd);
+        const double sn = fma(s, cd, c * sd);
+        c = fma(c, cd, -(s * sd));
+        s = sn;
+        // Newton's residual after this step is ~ (e/2) delta^2 (f'' = e sin E): stop once that is below
+        // 1e-15 rad -- tighter than the reference's |delta| < 1e-12 exit (src/Sgp4.zig:693)
+        if (delta * delta * em < AZK(keplerTol)) break;
     }
 
     const double ecose = fma(axnl, c, aynl * s);
@@ -154,7 +154,7 @@ AZ_HD void sgp4_cell(ColFn col, double t, const GravConsts &g, CellOut &o) {
         argpm = argpdf - tho;
         // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle, rotate instead of a second reduction
         double sd, cd;
-        if (fabs(tho) <= 0.78) sincos_quarter(tho, sd, cd);
+        if (fabs(tho) <= AZK(quarterLimit)) sincos_quarter(tho, sd, cd);
         else sincos_full(tho, sd, cd);
         const double sinmm = fma(sm, cd, cm * sd);
         const double t3 = t2 * t;
@@ -165,7 +165,7 @@ AZ_HD void sgp4_cell(ColFn col, double t, const GravConsts &g, CellOut &o) {
     }
 
     const double am = col(kAbase) * tempa * tempa;
-    const double em = fmax(col(kEcco) - tempe, 1.0e-6);
+    const double em = fmax(col(kEcco) - tempe, AZK(emFloor));
     mm = fma(col(kNo), templ, mm);
 
     kepler_posvel(am, em, mm, argpm, nodem, col(kSinio), col(kCosio), col(kAycof), col(kXlcof), col(kCon41),

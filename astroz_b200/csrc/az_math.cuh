@@ -39,6 +39,36 @@ AZ_HD double dbl_xor_hi(double x, unsigned mask) {  // flip bits of the high wor
 constexpr double kPi = 3.14159265358979323846264338327950288;
 constexpr double kTwoPi = 6.28318530717958647692528676655900577;
 
+// Every fp64 literal whose low 32 bits are non-zero lives in __constant__ memory: fp64 instructions take
+// constant-bank operands (c[bank][offset]) for free, whereas an immediate costs two UMOV / IMAD.MOV issue
+// slots each time it is materialised -- ncu showed ~230 of 739 instructions per cell were exactly that
+// (profiles/r01_sgp4_grid_notes.md), making the kernel issue-bound instead of fp64-pipe-bound.
+struct MathTable {
+    double s1, s2, s3, s4, s5, s6;          // fdlibm __kernel_sin
+    double c1, c2, c3, c4, c5, c6;          // fdlibm __kernel_cos
+    double twoOverPi, pio2Hi, pio2Mid, pio2Lo;
+    double ts3, ts5, ts7, tc4, tc6, tc8;    // truncated Taylor series for |x| <= 0.05
+    double quarterLimit, tinyLimit, clamp, emFloor, keplerTol, invTwoPi, twoPi, pi;
+};
+#define AZ_MATH_TABLE_INIT                                                                                    \
+    {                                                                                                         \
+        -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,                 \
+            2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,              \
+            4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,              \
+            -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,             \
+            6.36619772367581382433e-01, 1.57079632679489655800e+00, 6.12323399573676603587e-17,               \
+            -1.49738490485916983692e-33, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 24.0, -1.0 / 720.0,    \
+            1.0 / 40320.0, 0.78, 0.05, 0.95, 1.0e-6, 2.0e-15, 1.0 / 6.28318530717958647692528676655900577,    \
+            6.28318530717958647692528676655900577, 3.14159265358979323846264338327950288                      \
+    }
+static __constant__ MathTable kMathDev = AZ_MATH_TABLE_INIT;
+static const MathTable kMathHost = AZ_MATH_TABLE_INIT;
+#ifdef __CUDA_ARCH__
+#define AZK(name) (::az::kMathDev.name)
+#else
+#define AZK(name) (::az::kMathHost.name)
+#endif
+
 // ---- reciprocal -------------------------------------------------------------------------------
 AZ_HD double rcp_seed(double x) {
 #ifdef __CUDA_ARCH__
@@ -102,36 +132,32 @@ AZ_HD double sqrt_(double x) { return sqrt_from_rsqrt(x, rsqrt_nr(x)); }
 // ---- sin / cos --------------------------------------------------------------------------------
 // fdlibm __kernel_sin / __kernel_cos coefficients (public domain, Sun Microsystems), |r| <= pi/4.
 AZ_HD double ksin(double r, double r2) {
-    double p = fma(r2, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    p = fma(p, r2, 2.75573137070700676789e-06);
-    p = fma(p, r2, -1.98412698298579493134e-04);
-    p = fma(p, r2, 8.33333333332248946124e-03);
-    p = fma(p, r2, -1.66666666666666324348e-01);
+    double p = fma(r2, AZK(s6), AZK(s5));
+    p = fma(p, r2, AZK(s4));
+    p = fma(p, r2, AZK(s3));
+    p = fma(p, r2, AZK(s2));
+    p = fma(p, r2, AZK(s1));
     return fma(p, r2 * r, r);
 }
 AZ_HD double kcos(double r2) {
-    double p = fma(r2, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    p = fma(p, r2, -2.75573143513906633035e-07);
-    p = fma(p, r2, 2.48015872894767294178e-05);
-    p = fma(p, r2, -1.38888888888741095749e-03);
-    p = fma(p, r2, 4.16666666666666019037e-02);
+    double p = fma(r2, AZK(c6), AZK(c5));
+    p = fma(p, r2, AZK(c4));
+    p = fma(p, r2, AZK(c3));
+    p = fma(p, r2, AZK(c2));
+    p = fma(p, r2, AZK(c1));
     p = fma(p, r2, -0.5);
     return fma(p, r2, 1.0);
 }
 
 // sin and cos of x, |x| <~ 1e5.  Cody-Waite with pi/2 split in three (FMA keeps k*hi exact enough).
 AZ_HD void sincos_full(double x, double &s, double &c) {
-    constexpr double kTwoOverPi = 6.36619772367581382433e-01;
-    constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick
-    constexpr double kPio2Hi = 1.57079632679489655800e+00;
-    constexpr double kPio2Mid = 6.12323399573676603587e-17;
-    constexpr double kPio2Lo = -1.49738490485916983692e-33;
-    double kf = fma(x, kTwoOverPi, kMagic);
+    constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick (imm32-encodable)
+    double kf = fma(x, AZK(twoOverPi), kMagic);
     const unsigned q = (unsigned)dbl_lo(kf);
     kf -= kMagic;
-    double r = fma(kf, -kPio2Hi, x);
-    r = fma(kf, -kPio2Mid, r);
-    r = fma(kf, -kPio2Lo, r);
+    double r = fma(-kf, AZK(pio2Hi), x);
+    r = fma(-kf, AZK(pio2Mid), r);
+    r = fma(-kf, AZK(pio2Lo), r);
     double r2 = r * r;
     double sr = ksin(r, r2);
     double cr = kcos(r2);
@@ -153,11 +179,11 @@ AZ_HD void sincos_quarter(double x, double &s, double &c) {
 // (|x| <= 1.5 * 0.5 * j2 / pl^2 ~ 8e-4 for any orbit above the surface).
 AZ_HD void sincos_tiny(double x, double &s, double &c) {
     double x2 = x * x;
-    double p = fma(x2, -1.0 / 5040.0, 1.0 / 120.0);
-    p = fma(x2, p, -1.0 / 6.0);
+    double p = fma(x2, AZK(ts7), AZK(ts5));
+    p = fma(x2, p, AZK(ts3));
     s = fma(x * x2, p, x);
-    double q = fma(x2, 1.0 / 40320.0, -1.0 / 720.0);
-    q = fma(x2, q, 1.0 / 24.0);
+    double q = fma(x2, AZK(tc8), AZK(tc6));
+    q = fma(x2, q, AZK(tc4));
     q = fma(x2, q, -0.5);
     c = fma(x2, q, 1.0);
 }
@@ -171,17 +197,17 @@ AZ_HD void rotate(double s0, double c0, double sd, double cd, double &s, double 
 // sin/cos(a + d) for an arbitrary d, picking the cheapest exact-enough evaluation of (sin d, cos d)
 AZ_HD void rotate_small(double s0, double c0, double d, double &s, double &c) {
     double sd, cd;
-    if (fabs(d) <= 0.05) sincos_tiny(d, sd, cd);
+    if (fabs(d) <= AZK(tinyLimit)) sincos_tiny(d, sd, cd);
     else sincos_full(d, sd, cd);  // never taken for physical orbits; keeps the identity exact
     rotate(s0, c0, sd, cd, s, c);
 }
 
 // floored modulo 2*pi (Zig @mod semantics), result in [0, 2pi)
 AZ_HD double mod_twopi(double x) {
-    double n = floor(x * (1.0 / kTwoPi));
-    double r = fma(-kTwoPi, n, x);
-    r = (r < 0.0) ? r + kTwoPi : r;
-    return (r >= kTwoPi) ? r - kTwoPi : r;
+    double n = floor(x * AZK(invTwoPi));
+    double r = fma(-n, AZK(twoPi), x);
+    r = (r < 0.0) ? r + AZK(twoPi) : r;
+    return (r >= AZK(twoPi)) ? r - AZK(twoPi) : r;
 }
 
 // accurate atan2 for the SDP4 Lyddane branch only (rare): CUDA's own
