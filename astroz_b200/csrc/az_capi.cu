@@ -90,7 +90,7 @@ struct Constellation {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t chunkDone[64] = {};
     bool timed = false;
-    int variant = 0;
+    int variant = -1;  // -1 = shipped default; >= 0 selects a tuning variant (ASTROZ_SGP4_VARIANT)
     int chunks = 8;
 
     ~Constellation() {

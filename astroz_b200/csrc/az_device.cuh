@@ -35,141 +35,232 @@ struct CellOut {
 };
 
 // ---- Kepler solve + short-period terms + orientation -> r, v  (src/Sgp4.zig:646-750) ---------------
+// Written over kN independent cells of ONE satellite (kN epochs per thread): every statement is a
+// fully unrolled lane loop, so the per-satellite operands are fetched once for kN cells and the
+// scheduler interleaves kN dependency chains (ILP) on the half-rate fp64 pipe.
 // Differences from the reference's SIMD formulation, none of which changes the value beyond rounding:
 //   * no mod-2pi anywhere: every angle goes straight into a range-reducing sincos;
-//   * Newton iterates on the offset eps = E - u (|eps| <= e); sin/cos(E) come from rotating
-//     sin/cos(u) by eps with the pi/4 kernels -- one full sincos for the whole solve;
+//   * ONE full sincos for the whole Kepler solve: each Newton step is applied to (sin E, cos E) as a
+//     rotation by the step (9-op series below 0.05 rad); the loop stops when Newton's residual
+//     (e/2) delta^2 is below 1e-15 rad (the reference stops at |delta| < 1e-12);
 //   * no atan2: (sinu, cosu) is already a unit vector, the J2 short-period angle is applied as a
 //     rotation, and so is the inclination correction (sinio/cosio are per-satellite constants);
 //   * sqrt(pl) = sqrt(am)*betal, 1/pl and am^-1.5 come from the two rsqrt seeds already needed.
-AZ_HD void kepler_posvel(double am, double em, double mm, double argpm, double nodem,
-                                              double sinio, double cosio, double aycof, double xlcof, double con41,
-                                              double x1mth2, double x7thm1, const GravConsts &g, CellOut &o) {
-    const double ya = rsqrt_nr(am);                        // am^-1/2
-    const double inv_am = ya * ya;
-    const double temp = inv_am * rcp(fma(-em, em, 1.0));  // 1 / (am (1 - em^2))
-    double sa, ca;
-    sincos_full(argpm, sa, ca);
-    const double axnl = em * ca;
-    const double aynl = fma(em, sa, temp * aycof);
-    const double u = mm + argpm + temp * xlcof * axnl;  // xl - nodem, src/Sgp4.zig:680-682
+#define AZ_LANES _Pragma("unroll") for (int k = 0; k < kN; ++k)
 
-    double s, c;
-    sincos_full(u, s, c);
-    double eps = 0.0;
+struct SatAngles {  // inclination-dependent per-satellite (SGP4) or per-cell (SDP4) terms
+    double sinio, cosio, aycof, xlcof, con41, x1mth2, x7thm1;
+};
+
+template <int kN>
+AZ_HD void rotate_small_n(const double (&s0)[kN], const double (&c0)[kN], const double (&d)[kN], double (&s)[kN],
+                          double (&c)[kN]) {
+    bool big = false;
+    AZ_LANES big |= fabs(d[k]) > AZK(microLimit);
+    if (!big) {
+        AZ_LANES {
+            double sd, cd;
+            sincos_micro(d[k], sd, cd);
+            rotate(s0[k], c0[k], sd, cd, s[k], c[k]);
+        }
+    } else {  // never taken for physical orbits; keeps the identity exact
+        AZ_LANES {
+            double sd, cd;
+            sincos_full(d[k], sd, cd);
+            rotate(s0[k], c0[k], sd, cd, s[k], c[k]);
+        }
+    }
+}
+
+template <int kN>
+AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const double (&mm)[kN],
+                         const double (&argpm)[kN], const double (&nodem)[kN], const SatAngles (&sa)[kN],
+                         const GravConsts &g, CellOut (&o)[kN]) {
+    double ya[kN], inv_am[kN], axnl[kN], aynl[kN], s[kN], c[kN], eps[kN];
+    AZ_LANES {
+        ya[k] = rsqrt_nr(am[k]);  // am^-1/2
+        inv_am[k] = ya[k] * ya[k];
+        // 1 / (am (1 - em^2)); only scales the 1e-3-sized J3 terms, so the 2^-46 reciprocal is ample
+        const double temp = inv_am[k] * rcp_fast(fma(-em[k], em[k], 1.0));
+        double sw, cw;
+        sincos_full(argpm[k], sw, cw);
+        axnl[k] = em[k] * cw;
+        aynl[k] = fma(em[k], sw, temp * sa[k].aycof);
+        const double u = mm[k] + argpm[k] + temp * sa[k].xlcof * axnl[k];  // xl - nodem, src/Sgp4.zig:680-682
+        sincos_full(u, s[k], c[k]);
+        eps[k] = 0.0;
+    }
 #pragma unroll 1
     for (int it = 0; it < 10; ++it) {  // src/Sgp4.zig:687-694
-        const double esine = fma(axnl, s, -(aynl * c));
-        const double ecose = fma(axnl, c, aynl * s);
-        double delta = (esine - eps) * rcp_fast(1.0 - ecose);
-        delta = fmin(fmax(delta, -AZK(clamp)), AZK(clamp));
-        eps += delta;
-        // rotate (sin E, cos E) by the Newton step; a step below 0.05 rad uses the 9-op series
-        double sd, cd;
-        if (fabs(delta) <= AZK(tinyLimit)) sincos_tiny(delta, sd, cd);
-        else sincos_full(delta, sd, cd);
-        const double sn = fma(s, cd, c * sd);
-        c = fma(c, cd, -(s * sd));
-        s = sn;
-        // Newton's residual after this step is ~ (e/2) delta^2 (f'' = e sin E): stop once that is below
-        // 1e-15 rad -- tighter than the reference's |delta| < 1e-12 exit (src/Sgp4.zig:693)
-        if (delta * delta * em < AZK(keplerTol)) break;
+        double delta[kN];
+        bool big = false, done = true, linear = true;
+        AZ_LANES {
+            const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
+            const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
+            double d = (esine - eps[k]) * rcp_fast(1.0 - ecose);
+            d = fmin(fmax(d, -AZK(clamp)), AZK(clamp));
+            eps[k] += d;
+            delta[k] = d;
+            const double ad = fabs(d);
+            big |= ad > AZK(tinyLimit);
+            linear &= ad < AZK(linearLimit);
+            // Newton's residual after this step is ~ (e/2) delta^2 (f'' = e sin E)
+            done &= d * d * em[k] < AZK(keplerTol);
+        }
+        if (linear) {  // |delta| < 1e-8: first-order update is exact to 5e-17 and the solve is finished
+            AZ_LANES {
+                const double sn = fma(c[k], delta[k], s[k]);
+                c[k] = fma(-s[k], delta[k], c[k]);
+                s[k] = sn;
+            }
+            break;
+        }
+        if (!big) {
+            AZ_LANES {
+                double sd, cd;
+                sincos_tiny(delta[k], sd, cd);
+                const double sn = fma(s[k], cd, c[k] * sd);
+                c[k] = fma(c[k], cd, -(s[k] * sd));
+                s[k] = sn;
+            }
+        } else {
+            AZ_LANES {
+                double sd, cd;
+                sincos_full(delta[k], sd, cd);
+                const double sn = fma(s[k], cd, c[k] * sd);
+                c[k] = fma(c[k], cd, -(s[k] * sd));
+                s[k] = sn;
+            }
+        }
+        if (done) break;
     }
 
-    const double ecose = fma(axnl, c, aynl * s);
-    const double esine = fma(axnl, s, -(aynl * c));
-    const double omel2 = 1.0 - fma(axnl, axnl, aynl * aynl);
-    const double yb = rsqrt_nr(omel2);
-    const double betal = sqrt_from_rsqrt(omel2, yb);
-    const double sqa = sqrt_from_rsqrt(am, ya);
-    const double rl = am * (1.0 - ecose);
-    const double irl = rcp(rl);
-    const double rdotl = sqa * esine * irl;
-    const double rvdotl = sqa * betal * irl;  // sqrt(pl) / rl
-    const double aor = am * irl;
-    const double est = esine * rcp(1.0 + betal);
-    const double sinu = aor * (s - aynl - axnl * est);
-    const double cosu = aor * (c - axnl + aynl * est);
-    const double sin2u = 2.0 * sinu * cosu;
-    const double cos2u = fma(-2.0 * sinu, sinu, 1.0);
+    double sinu[kN], cosu[kN], dsu[kN], dinc[kN], xnode[kN], mrt[kN], mvt[kN], rvdot[kN];
+    AZ_LANES {
+        const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
+        const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
+        const double omel2 = 1.0 - fma(axnl[k], axnl[k], aynl[k] * aynl[k]);
+        const double yb = rsqrt_nr(omel2);
+        const double betal = sqrt_from_rsqrt(omel2, yb);
+        const double sqa = sqrt_from_rsqrt(am[k], ya[k]);
+        const double rl = am[k] * (1.0 - ecose);
+        const double irl = rcp(rl);
+        const double rdotl = sqa * esine * irl;
+        const double rvdotl = sqa * betal * irl;  // sqrt(pl) / rl
+        const double aor = am[k] * irl;
+        const double est = esine * rcp_fast(1.0 + betal);  // multiplies e-sized terms only
+        sinu[k] = aor * (s[k] - aynl[k] - axnl[k] * est);
+        cosu[k] = aor * (c[k] - axnl[k] + aynl[k] * est);
+        const double sin2u = 2.0 * sinu[k] * cosu[k];
+        const double cos2u = fma(-2.0 * sinu[k], sinu[k], 1.0);
 
-    const double ipl = inv_am * (yb * yb);  // 1 / pl
-    const double temp1 = 0.5 * g.j2 * ipl;
-    const double temp2 = temp1 * ipl;
-    const double w = inv_am * ya;  // nm / xke = am^-3/2
+        const double ipl = inv_am[k] * (yb * yb);  // 1 / pl
+        const double temp1 = 0.5 * g.j2 * ipl;
+        const double temp2 = temp1 * ipl;
+        const double w = inv_am[k] * ya[k];  // nm / xke = am^-3/2
+        mrt[k] = fma(rl, fma(-1.5 * temp2 * betal, sa[k].con41, 1.0), 0.5 * temp1 * sa[k].x1mth2 * cos2u);
+        dsu[k] = -0.25 * temp2 * sa[k].x7thm1 * sin2u;
+        const double t2c = 1.5 * temp2 * sa[k].cosio;
+        xnode[k] = fma(t2c, sin2u, nodem[k]);
+        dinc[k] = t2c * sa[k].sinio * cos2u;
+        const double wt1 = w * temp1;
+        mvt[k] = fma(-wt1 * sa[k].x1mth2, sin2u, rdotl);
+        rvdot[k] = fma(wt1, fma(sa[k].x1mth2, cos2u, 1.5 * sa[k].con41), rvdotl);
+    }
 
-    const double mrt = fma(rl, fma(-1.5 * temp2 * betal, con41, 1.0), 0.5 * temp1 * x1mth2 * cos2u);
-    const double dsu = -0.25 * temp2 * x7thm1 * sin2u;
-    const double t2c = 1.5 * temp2 * cosio;
-    const double dnode = t2c * sin2u;
-    const double dinc = t2c * sinio * cos2u;
-    const double wt1 = w * temp1;
-    const double mvt = fma(-wt1 * x1mth2, sin2u, rdotl);
-    const double rvdot = fma(wt1, fma(x1mth2, cos2u, 1.5 * con41), rvdotl);
-
-    double sinsu, cossu, snod, cnod, sini, cosi;
-    rotate_small(sinu, cosu, dsu, sinsu, cossu);
-    sincos_full(nodem + dnode, snod, cnod);
-    rotate_small(sinio, cosio, dinc, sini, cosi);
-
-    const double xmx = -snod * cosi;
-    const double xmy = cnod * cosi;
-    const double ux = fma(xmx, sinsu, cnod * cossu);
-    const double uy = fma(xmy, sinsu, snod * cossu);
-    const double uz = sini * sinsu;
-    const double vx = fma(xmx, cossu, -(cnod * sinsu));
-    const double vy = fma(xmy, cossu, -(snod * sinsu));
-    const double vz = sini * cossu;
-
-    const double rs = mrt * g.radiusEarthKm;
-    o.rx = rs * ux;
-    o.ry = rs * uy;
-    o.rz = rs * uz;
-    o.vx = fma(mvt, ux, rvdot * vx) * g.vkmpersec;
-    o.vy = fma(mvt, uy, rvdot * vy) * g.vkmpersec;
-    o.vz = fma(mvt, uz, rvdot * vz) * g.vkmpersec;
-    o.mrt = mrt;
+    double sinsu[kN], cossu[kN], sini[kN], cosi[kN], si0[kN], ci0[kN];
+    AZ_LANES {
+        si0[k] = sa[k].sinio;
+        ci0[k] = sa[k].cosio;
+    }
+    rotate_small_n<kN>(sinu, cosu, dsu, sinsu, cossu);
+    rotate_small_n<kN>(si0, ci0, dinc, sini, cosi);
+    AZ_LANES {
+        double snod, cnod;
+        sincos_full(xnode[k], snod, cnod);
+        const double xmx = -snod * cosi[k];
+        const double xmy = cnod * cosi[k];
+        const double ux = fma(xmx, sinsu[k], cnod * cossu[k]);
+        const double uy = fma(xmy, sinsu[k], snod * cossu[k]);
+        const double uz = sini[k] * sinsu[k];
+        const double vx = fma(xmx, cossu[k], -(cnod * sinsu[k]));
+        const double vy = fma(xmy, cossu[k], -(snod * sinsu[k]));
+        const double vz = sini[k] * cossu[k];
+        const double rs = mrt[k] * g.radiusEarthKm;
+        o[k].rx = rs * ux;
+        o[k].ry = rs * uy;
+        o[k].rz = rs * uz;
+        o[k].vx = fma(mvt[k], ux, rvdot[k] * vx) * g.vkmpersec;
+        o[k].vy = fma(mvt[k], uy, rvdot[k] * vy) * g.vkmpersec;
+        o[k].vz = fma(mvt[k], uz, rvdot[k] * vz) * g.vkmpersec;
+        o[k].mrt = mrt[k];
+    }
 }
 
 // ---- near-earth secular + drag update, then the shared core (src/Sgp4Batch.zig:113-157) -----------
-// `col(i)` returns column i of the satellite handled by this warp (shared-memory broadcast read).
-template <typename ColFn>
-AZ_HD void sgp4_cell(ColFn col, double t, const GravConsts &g, CellOut &o) {
-    const double t2 = t * t;
-    const double xmdf = fma(col(kMdot), t, col(kMo));
-    const double argpdf = fma(col(kArgpdot), t, col(kArgpo));
-    const double nodem = fma(col(kXnodcf), t2, fma(col(kNodedot), t, col(kNodeo)));
-    double tempa = fma(-col(kCc1), t, 1.0);
-    double tempe = col(kBc4) * t;
-    double templ = col(kT2cof) * t2;
-    double mm = xmdf, argpm = argpdf;
-
-    if (col(kIsimp) == 0.0) {  // warp-uniform: a warp works on one satellite (src/Sgp4Batch.zig:133-145)
-        double sm, cm;
-        sincos_full(xmdf, sm, cm);
-        const double dm = fma(col(kEta), cm, 1.0);
-        const double delm = col(kXmcof) * (dm * dm * dm - col(kDelmo));
-        const double tho = fma(col(kOmgcof), t, delm);
-        mm = xmdf + tho;
-        argpm = argpdf - tho;
-        // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle, rotate instead of a second reduction
-        double sd, cd;
-        if (fabs(tho) <= AZK(quarterLimit)) sincos_quarter(tho, sd, cd);
-        else sincos_full(tho, sd, cd);
-        const double sinmm = fma(sm, cd, cm * sd);
-        const double t3 = t2 * t;
-        const double t4 = t3 * t;
-        tempa = tempa - col(kD2) * t2 - col(kD3) * t3 - col(kD4) * t4;
-        tempe = fma(col(kBc5), sinmm - col(kSinmao), tempe);
-        templ = templ + col(kT3cof) * t3 + t4 * fma(t, col(kT5cof), col(kT4cof));
+// `col(i)` returns column i of the satellite handled by this warp (shared-memory broadcast read);
+// t[] are kN epochs (minutes since the element epoch) of that one satellite.
+template <int kN, typename ColFn>
+AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, CellOut (&o)[kN]) {
+    double t2[kN], xmdf[kN], argpm[kN], nodem[kN], tempa[kN], tempe[kN], templ[kN], mm[kN];
+    {
+        const double mdot = col(kMdot), mo = col(kMo), argpdot = col(kArgpdot), argpo = col(kArgpo);
+        const double xnodcf = col(kXnodcf), nodedot = col(kNodedot), nodeo = col(kNodeo);
+        const double cc1 = col(kCc1), bc4 = col(kBc4), t2cof = col(kT2cof);
+        AZ_LANES {
+            t2[k] = t[k] * t[k];
+            xmdf[k] = fma(mdot, t[k], mo);
+            argpm[k] = fma(argpdot, t[k], argpo);
+            nodem[k] = fma(xnodcf, t2[k], fma(nodedot, t[k], nodeo));
+            tempa[k] = fma(-cc1, t[k], 1.0);
+            tempe[k] = bc4 * t[k];
+            templ[k] = t2cof * t2[k];
+            mm[k] = xmdf[k];
+        }
     }
-
-    const double am = col(kAbase) * tempa * tempa;
-    const double em = fmax(col(kEcco) - tempe, AZK(emFloor));
-    mm = fma(col(kNo), templ, mm);
-
-    kepler_posvel(am, em, mm, argpm, nodem, col(kSinio), col(kCosio), col(kAycof), col(kXlcof), col(kCon41),
-                  col(kX1mth2), col(kX7thm1), g, o);
+    if (col(kIsimp) == 0.0) {  // warp-uniform: a warp works on one satellite (src/Sgp4Batch.zig:133-145)
+        const double eta = col(kEta), xmcof = col(kXmcof), delmo = col(kDelmo), omgcof = col(kOmgcof);
+        const double d2 = col(kD2), d3 = col(kD3), d4 = col(kD4), bc5 = col(kBc5), sinmao = col(kSinmao);
+        const double t3cof = col(kT3cof), t4cof = col(kT4cof), t5cof = col(kT5cof);
+        double sm[kN], cm[kN], tho[kN];
+        bool big = false;
+        AZ_LANES {
+            sincos_full(xmdf[k], sm[k], cm[k]);
+            const double dm = fma(eta, cm[k], 1.0);
+            const double delm = xmcof * (dm * dm * dm - delmo);
+            tho[k] = fma(omgcof, t[k], delm);
+            mm[k] = xmdf[k] + tho[k];
+            argpm[k] -= tho[k];
+            big |= fabs(tho[k]) > AZK(quarterLimit);
+        }
+        AZ_LANES {
+            // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle, rotate instead of a second reduction
+            double sd, cd;
+            if (!big) sincos_quarter(tho[k], sd, cd);
+            else sincos_full(tho[k], sd, cd);
+            const double sinmm = fma(sm[k], cd, cm[k] * sd);
+            const double t3 = t2[k] * t[k];
+            const double t4 = t3 * t[k];
+            tempa[k] = tempa[k] - d2 * t2[k] - d3 * t3 - d4 * t4;
+            tempe[k] = fma(bc5, sinmm - sinmao, tempe[k]);
+            templ[k] = templ[k] + t3cof * t3 + t4 * fma(t[k], t5cof, t4cof);
+        }
+    }
+    double am[kN], em[kN];
+    SatAngles sa[kN];
+    {
+        const double abase = col(kAbase), ecco = col(kEcco), no = col(kNo);
+        SatAngles a0;
+        a0.sinio = col(kSinio); a0.cosio = col(kCosio); a0.aycof = col(kAycof); a0.xlcof = col(kXlcof);
+        a0.con41 = col(kCon41); a0.x1mth2 = col(kX1mth2); a0.x7thm1 = col(kX7thm1);
+        AZ_LANES {
+            am[k] = abase * tempa[k] * tempa[k];
+            em[k] = fmax(ecco - tempe[k], AZK(emFloor));
+            mm[k] = fma(no, templ[k], mm[k]);
+            sa[k] = a0;
+        }
+    }
+    kepler_posvel<kN>(am, em, mm, argpm, nodem, sa, g, o);
 }
 
 // ---- deep space (src/Sdp4Batch.zig:16-125,199-526; src/Sdp4.zig:681-866) --------------------------------
@@ -345,8 +436,13 @@ AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double a
     const double aycof = -0.5 * g.j3oj2 * sinip;
     const double den = 1.0 + cosip;
     const double xlcof = -0.25 * g.j3oj2 * sinip * fma(5.0, cosip, 3.0) * rcp(fabs(den) > 1.5e-12 ? den : 1.5e-12);
-    kepler_posvel(am, em, mm, argpm, nodem, sinip, cosip, aycof, xlcof, fma(3.0, cosip2, -1.0), 1.0 - cosip2,
-                  fma(7.0, cosip2, -1.0), g, o);
+    const double am1[1] = {am}, em1[1] = {em}, mm1[1] = {mm}, ar1[1] = {argpm}, no1[1] = {nodem};
+    SatAngles sa[1];
+    sa[0].sinio = sinip; sa[0].cosio = cosip; sa[0].aycof = aycof; sa[0].xlcof = xlcof;
+    sa[0].con41 = fma(3.0, cosip2, -1.0); sa[0].x1mth2 = 1.0 - cosip2; sa[0].x7thm1 = fma(7.0, cosip2, -1.0);
+    CellOut o1[1];
+    kepler_posvel<1>(am1, em1, mm1, ar1, no1, sa, g, o1);
+    o = o1[0];
     return (o.mrt < 1.0) ? 1 : 0;
 }
 

@@ -78,7 +78,7 @@ __device__ __forceinline__ void store_cell(const GridArgs &a, uint32_t row, uint
 // ---------------------------------------------------------------------------------------------------
 // K1: near-earth grid
 // ---------------------------------------------------------------------------------------------------
-template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks>
+template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(const GridArgs a) {
     __shared__ __align__(128) double tile[kSgp4TileDoubles];
     __shared__ __align__(8) uint64_t bar;
@@ -106,54 +106,80 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
         auto col = [colBase](int i) { return colBase[i * kTileSats]; };
         const double toff = __ldg(a.toff + sat);
         const uint32_t row = __ldg(a.orig + sat);
+        // a thread owns kLanes epochs of this satellite, 32 apart, so each warp-level store still covers 32
+        // consecutive epochs (one contiguous 768-byte run of the satellite-major block)
 #pragma unroll 1
-        for (uint32_t t = t0 + lane; t < t1; t += 32) {
-            const double ts = __ldg(a.tbase + t) + toff;  // src/Constellation.zig:425
-            CellOut o;
-            sgp4_cell(col, ts, a.g, o);
-            if (a.status) a.status[(size_t)row * a.nTimes + t] = (o.mrt < 1.0) ? 1 : 0;
-            store_cell<kLayout, kMode, kVel>(a, row, t, o);
+        for (uint32_t t = t0 + lane; t < t1; t += 32 * kLanes) {
+            double ts[kLanes];
+#pragma unroll
+            for (int k = 0; k < kLanes; ++k)
+                ts[k] = __ldg(a.tbase + min(t + 32u * k, t1 - 1)) + toff;  // src/Constellation.zig:425
+            CellOut o[kLanes];
+            sgp4_cell<kLanes>(col, ts, a.g, o);
+#pragma unroll
+            for (int k = 0; k < kLanes; ++k) {
+                const uint32_t tk = t + 32u * k;
+                if (k == 0 || tk < t1) {
+                    if (a.status) a.status[(size_t)row * a.nTimes + tk] = (o[k].mrt < 1.0) ? 1 : 0;
+                    store_cell<kLayout, kMode, kVel>(a, row, tk, o[k]);
+                }
+            }
         }
     }
 }
 
 struct Sgp4Variant {
     const char *name;
-    int warps, stripe, minBlocks;
+    int warps, stripe, minBlocks, lanes;
 };
+// variant 0 is the shipped configuration; the rest exist for on-device tuning sweeps (tools/sweep_variants.py)
 static const Sgp4Variant kVariants[] = {
-    {"w4_s256_b4", 4, 256, 4}, {"w4_s256_b3", 4, 256, 3}, {"w8_s256_b2", 8, 256, 2},
-    {"w4_s128_b5", 4, 128, 5}, {"w4_s512_b4", 4, 512, 4}, {"w8_s128_b3", 8, 128, 3},
-    {"w2_s256_b8", 2, 256, 8}, {"w4_s256_b2", 4, 256, 2},
+    {"w4_s256_b4_l1", 4, 256, 4, 1}, {"w4_s256_b3_l2", 4, 256, 3, 2}, {"w4_s512_b3_l2", 4, 512, 3, 2},
+    {"w4_s256_b2_l2", 4, 256, 2, 2}, {"w8_s256_b1_l2", 8, 256, 1, 2}, {"w4_s512_b4_l1", 4, 512, 4, 1},
+    {"w2_s256_b4_l2", 2, 256, 4, 2}, {"w4_s768_b3_l2", 4, 768, 3, 2}, {"w4_s768_b2_l3", 4, 768, 2, 3},
+    {"w8_s512_b2_l2", 8, 512, 2, 2}, {"w4_s256_b6_l1", 4, 256, 6, 1}, {"w4_s256_b7_l1", 4, 256, 7, 1},
+    {"w4_s256_b8_l1", 4, 256, 8, 1}, {"w8_s256_b4_l1", 8, 256, 4, 1}, {"w4_s256_b5_l2", 4, 256, 5, 2},
 };
 int sgp4_variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const char *sgp4_variant_name(int v) { return (v >= 0 && v < sgp4_variant_count()) ? kVariants[v].name : "?"; }
 
-template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks>
+template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes>
 static cudaError_t launch_k1(const GridArgs &a, cudaStream_t stream) {
     const uint32_t tiles = (a.nSats + kTileSats - 1) / kTileSats;
     const uint32_t stripes = (a.nTimes + kStripe - 1) / kStripe;
     if (tiles == 0 || stripes == 0) return cudaSuccess;
     dim3 grid(tiles, stripes);
-    sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks><<<grid, kWarps * 32, 0, stream>>>(a);
+    sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks, kLanes><<<grid, kWarps * 32, 0, stream>>>(a);
     return cudaGetLastError();
 }
+
+#ifndef AZ_DEFAULT_K1
+#define AZ_DEFAULT_K1 4, 256, 3, 2
+#endif
 
 template <int kLayout, int kMode, bool kVel>
 static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int variant) {
     if (kLayout == 0 && kMode == 0 && kVel) {  // tuning variants exist for the headline specialisation only
         switch (variant) {
-            case 1: return launch_k1<0, 0, true, 4, 256, 3>(a, stream);
-            case 2: return launch_k1<0, 0, true, 8, 256, 2>(a, stream);
-            case 3: return launch_k1<0, 0, true, 4, 128, 5>(a, stream);
-            case 4: return launch_k1<0, 0, true, 4, 512, 4>(a, stream);
-            case 5: return launch_k1<0, 0, true, 8, 128, 3>(a, stream);
-            case 6: return launch_k1<0, 0, true, 2, 256, 8>(a, stream);
-            case 7: return launch_k1<0, 0, true, 4, 256, 2>(a, stream);
+            case 0: return launch_k1<0, 0, true, 4, 256, 4, 1>(a, stream);
+            case 1: return launch_k1<0, 0, true, 4, 256, 3, 2>(a, stream);
+            case 2: return launch_k1<0, 0, true, 4, 512, 3, 2>(a, stream);
+            case 3: return launch_k1<0, 0, true, 4, 256, 2, 2>(a, stream);
+            case 4: return launch_k1<0, 0, true, 8, 256, 1, 2>(a, stream);
+            case 5: return launch_k1<0, 0, true, 4, 512, 4, 1>(a, stream);
+            case 6: return launch_k1<0, 0, true, 2, 256, 4, 2>(a, stream);
+            case 7: return launch_k1<0, 0, true, 4, 768, 3, 2>(a, stream);
+            case 8: return launch_k1<0, 0, true, 4, 768, 2, 3>(a, stream);
+            case 9: return launch_k1<0, 0, true, 8, 512, 2, 2>(a, stream);
+            case 10: return launch_k1<0, 0, true, 4, 256, 6, 1>(a, stream);
+            case 11: return launch_k1<0, 0, true, 4, 256, 7, 1>(a, stream);
+            case 12: return launch_k1<0, 0, true, 4, 256, 8, 1>(a, stream);
+            case 13: return launch_k1<0, 0, true, 8, 256, 4, 1>(a, stream);
+            case 14: return launch_k1<0, 0, true, 4, 256, 5, 2>(a, stream);
             default: break;
         }
     }
-    return launch_k1<kLayout, kMode, kVel, 4, 256, 4>(a, stream);
+    return launch_k1<kLayout, kMode, kVel, AZ_DEFAULT_K1>(a, stream);
 }
 
 cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant) {

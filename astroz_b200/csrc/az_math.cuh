@@ -48,7 +48,7 @@ struct MathTable {
     double c1, c2, c3, c4, c5, c6;          // fdlibm __kernel_cos
     double twoOverPi, pio2Hi, pio2Mid, pio2Lo;
     double ts3, ts5, ts7, tc4, tc6, tc8;    // truncated Taylor series for |x| <= 0.05
-    double quarterLimit, tinyLimit, clamp, emFloor, keplerTol, invTwoPi, twoPi, pi;
+    double quarterLimit, tinyLimit, clamp, emFloor, keplerTol, invTwoPi, twoPi, pi, microLimit, linearLimit;
 };
 #define AZ_MATH_TABLE_INIT                                                                                    \
     {                                                                                                         \
@@ -59,7 +59,7 @@ struct MathTable {
             6.36619772367581382433e-01, 1.57079632679489655800e+00, 6.12323399573676603587e-17,               \
             -1.49738490485916983692e-33, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 24.0, -1.0 / 720.0,    \
             1.0 / 40320.0, 0.78, 0.05, 0.95, 1.0e-6, 2.0e-15, 1.0 / 6.28318530717958647692528676655900577,    \
-            6.28318530717958647692528676655900577, 3.14159265358979323846264338327950288                      \
+            6.28318530717958647692528676655900577, 3.14159265358979323846264338327950288, 2.0e-3, 1.0e-8      \
     }
 static __constant__ MathTable kMathDev = AZ_MATH_TABLE_INIT;
 static const MathTable kMathHost = AZ_MATH_TABLE_INIT;
@@ -149,15 +149,14 @@ AZ_HD double kcos(double r2) {
     return fma(p, r2, 1.0);
 }
 
-// sin and cos of x, |x| <~ 1e5.  Cody-Waite with pi/2 split in three (FMA keeps k*hi exact enough).
+// sin and cos of x, |x| <~ 1e5.  Cody-Waite with pi/2 = hi + mid (FMA keeps k*hi exact enough).
 AZ_HD void sincos_full(double x, double &s, double &c) {
     constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick (imm32-encodable)
     double kf = fma(x, AZK(twoOverPi), kMagic);
     const unsigned q = (unsigned)dbl_lo(kf);
     kf -= kMagic;
     double r = fma(-kf, AZK(pio2Hi), x);
-    r = fma(-kf, AZK(pio2Mid), r);
-    r = fma(-kf, AZK(pio2Lo), r);
+    r = fma(-kf, AZK(pio2Mid), r);  // third part of pi/2 (-1.5e-33 * k) is < 1e-17 for every |x| < 1e15
     double r2 = r * r;
     double sr = ksin(r, r2);
     double cr = kcos(r2);
@@ -186,6 +185,13 @@ AZ_HD void sincos_tiny(double x, double &s, double &c) {
     q = fma(x2, q, AZK(tc4));
     q = fma(x2, q, -0.5);
     c = fma(x2, q, 1.0);
+}
+
+// |x| <= 2e-3 (the J2 short-period angles of any orbit above the surface are < 1e-3): abs error < 3e-16 |x|
+AZ_HD void sincos_micro(double x, double &s, double &c) {
+    double x2 = x * x;
+    s = fma(x * x2, AZK(ts3), x);
+    c = fma(x2, fma(x2, AZK(tc4), -0.5), 1.0);
 }
 
 // rotate the unit vector (s0, c0) = (sin a, cos a) by angle d given (sd, cd): returns sin/cos(a + d)

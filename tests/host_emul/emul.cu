@@ -9,6 +9,9 @@
 
 using namespace az;  // (az::* names do not collide with CUDA math: rsqrt_nr, div_nr)
 
+static int g_lanes = 1;
+extern "C" void emul_set_lanes(int lanes) { g_lanes = lanes; }
+
 extern "C" int emul_constellation_propagate(const char *const *l1, const char *const *l2, uint32_t n, int grav,
                                             const double *jd, const double *fr, uint32_t nt, double *pos, double *vel,
                                             uint8_t *status) {
@@ -27,12 +30,24 @@ extern "C" int emul_constellation_propagate(const char *const *l1, const char *c
         auto col = [&](int i) { return tile[i * kTileSats + sl]; };
         const double toff = (cat.referenceEpochJd - cat.sgp4Epoch[s]) * 1440.0;
         const uint32_t orig = cat.sgp4Orig[s];
-        for (uint32_t t = 0; t < nt; ++t) {
-            CellOut o;
-            sgp4_cell(col, tbase[t] + toff, g, o);
-            double *p = pos + ((size_t)orig * nt + t) * 3, *v = vel + ((size_t)orig * nt + t) * 3;
-            p[0] = o.rx; p[1] = o.ry; p[2] = o.rz; v[0] = o.vx; v[1] = o.vy; v[2] = o.vz;
-            if (status) status[(size_t)orig * nt + t] = o.mrt < 1.0 ? 1 : 0;
+        for (uint32_t t = 0; t < nt; t += g_lanes) {
+            CellOut oo[2];
+            if (g_lanes == 2) {  // the kernel's 2-epochs-per-thread path (second lane clamped at the end)
+                const uint32_t tb = t + 1 < nt ? t + 1 : nt - 1;
+                const double ts[2] = {tbase[t] + toff, tbase[tb] + toff};
+                sgp4_cell<2>(col, ts, g, oo);
+            } else {
+                CellOut o1[1];
+                const double ts[1] = {tbase[t] + toff};
+                sgp4_cell<1>(col, ts, g, o1);
+                oo[0] = o1[0];
+            }
+            for (int k = 0; k < g_lanes && t + k < nt; ++k) {
+                const CellOut &o = oo[k];
+                double *p = pos + ((size_t)orig * nt + t + k) * 3, *v = vel + ((size_t)orig * nt + t + k) * 3;
+                p[0] = o.rx; p[1] = o.ry; p[2] = o.rz; v[0] = o.vx; v[1] = o.vy; v[2] = o.vz;
+                if (status) status[(size_t)orig * nt + t + k] = o.mrt < 1.0 ? 1 : 0;
+            }
         }
     }
     for (uint32_t s = 0; s < cat.nSdp4; ++s) {
