@@ -153,6 +153,22 @@ class Constellation:
             C.c_void_p(status.data_ptr()) if status is not None else None,
             int(outputMode), int(layout), rows, int(out_sat_offset), C.c_void_p(stream) if stream else None))
 
+    def propagate_gather(self, jd, fr, peer_pos=None, peer_vel=None, mc_pos: int = 0, mc_vel: int = 0,
+                         out_num_sats: int | None = None, out_sat_offset: int = 0, stream: int = 0) -> None:
+        """Fused propagate + all-gather (TEME, satellite-major): this constellation's rows are written into
+        every GPU's copy of the block from inside the kernels.  peer_pos / peer_vel: lists of raw device
+        pointers (ints) of the per-GPU mappings; mc_pos / mc_vel: NVLS multicast pointers (ints, 0 = use the
+        peer lists)."""
+        jd, fr = as_f64(jd), as_f64(fr)
+        rows = self.numSatellites if out_num_sats is None else int(out_num_sats)
+        n = len(peer_pos) if peer_pos else 0
+        pp = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in (peer_pos or [])])
+        pv = (C.c_void_p * max(n, 1))(*[C.c_void_p(int(p)) for p in (peer_vel or [])]) if peer_vel else None
+        check(lib().astroz_cuda_constellation_propagate_gather(
+            self._h, dptr(jd), dptr(fr), jd.shape[0], pp if n else None, pv, n,
+            C.c_void_p(mc_pos) if mc_pos else None, C.c_void_p(mc_vel) if mc_vel else None,
+            rows, int(out_sat_offset), C.c_void_p(stream) if stream else None))
+
     def synchronize(self) -> None:
         check(lib().astroz_cuda_constellation_synchronize(self._h))
 

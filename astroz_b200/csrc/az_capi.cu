@@ -195,8 +195,16 @@ struct Launch {  // one grid pass over (satellite range) x (time range)
 };
 
 // Queue the kernels for `L` on stream s.  Time arrays must already be on the device.
+struct GatherTargets {  // fused all-gather destinations (see astroz_cuda_constellation_propagate_gather)
+    int kind = 0;      // 0 none, 1 multicast, 2 peer stores
+    int nPeers = 0;
+    double *mcPos = nullptr, *mcVel = nullptr;
+    double *peerPos[az::kMaxPeers] = {}, *peerVel[az::kMaxPeers] = {};
+};
+
 int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *dPos, double *dVel, uint8_t *dStatus,
-                   int mode, int layout, uint32_t outNumSats, uint32_t outSatOffset, cudaStream_t s, bool timeIt) {
+                   int mode, int layout, uint32_t outNumSats, uint32_t outSatOffset, cudaStream_t s, bool timeIt,
+                   const GatherTargets *gt = nullptr) {
     const az::CatalogTables &t = c->cat;
     const size_t tcap = c->dTime.cap / 4;
     az::GridArgs a;
@@ -211,8 +219,18 @@ int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *
     size_t shift;
     if (layout == 0) shift = ((size_t)outSatOffset * ntTotal + L.t0) * 3;
     else shift = ((size_t)L.t0 * outNumSats + outSatOffset) * 3;
-    a.pos = dPos + shift;
+    a.pos = dPos ? dPos + shift : nullptr;
     a.vel = dVel ? dVel + shift : nullptr;
+    if (gt && gt->kind) {
+        a.gather = gt->kind;
+        a.nPeers = gt->nPeers;
+        a.mcPos = gt->mcPos ? gt->mcPos + shift : nullptr;
+        a.mcVel = gt->mcVel ? gt->mcVel + shift : nullptr;
+        for (int p = 0; p < gt->nPeers; ++p) {
+            a.peerPos[p] = gt->peerPos[p] ? gt->peerPos[p] + shift : nullptr;
+            a.peerVel[p] = gt->peerVel[p] ? gt->peerVel[p] + shift : nullptr;
+        }
+    }
     a.status = dStatus ? dStatus + (size_t)outSatOffset * ntTotal + L.t0 : nullptr;
     if (layout == 0 && L.nt != ntTotal) {
         g_lastError = "internal: satellite-major launches cover the whole time axis";
@@ -421,6 +439,48 @@ int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, con
     L.tileCount = c->cat.sgp4Tiles_count();
     L.nt = n_times;
     rc = queue_grid(c, L, n_times, d_pos, d_vel, d_status, mode, layout, out_num_sats, out_sat_offset, s, true);
+    c->timed = (rc == ASTROZ_OK);
+    return rc;
+}
+
+int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, const double *jd, const double *fr,
+                                                   uint32_t n_times, void *const *peer_pos, void *const *peer_vel,
+                                                   uint32_t n_peers, void *mc_pos, void *mc_vel, uint32_t out_num_sats,
+                                                   uint32_t out_sat_offset, void *stream) {
+    Constellation *c = static_cast<Constellation *>(h);
+    if (!c || !jd || !fr) return ASTROZ_NULL_POINTER;
+    if (!mc_pos && (!peer_pos || n_peers == 0)) return ASTROZ_NULL_POINTER;
+    if (n_peers > (uint32_t)az::kMaxPeers) {
+        g_lastError = "at most 8 peers (one NVSwitch domain)";
+        return ASTROZ_VALUE_ERROR;
+    }
+    if (n_times == 0 || c->cat.n == 0) return ASTROZ_OK;
+    if (out_num_sats < out_sat_offset + c->cat.n) {
+        g_lastError = "output block smaller than numSatellites rows";
+        return ASTROZ_DECAYED;
+    }
+    GatherTargets gt;
+    gt.kind = mc_pos ? 1 : 2;
+    gt.nPeers = (int)n_peers;
+    gt.mcPos = static_cast<double *>(mc_pos);
+    gt.mcVel = static_cast<double *>(mc_vel);
+    for (uint32_t p = 0; p < n_peers && peer_pos; ++p) {
+        gt.peerPos[p] = static_cast<double *>(peer_pos[p]);
+        gt.peerVel[p] = peer_vel ? static_cast<double *>(peer_vel[p]) : nullptr;
+        if (!gt.peerPos[p]) return ASTROZ_NULL_POINTER;
+    }
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    double jdMin, jdMax;
+    int32_t rc = upload_time_axis(c, jd, fr, n_times, ASTROZ_MODE_TEME, s, &jdMin, &jdMax);
+    if (rc != ASTROZ_OK) return rc;
+    rc = prepare_deep_space(c, jdMin, jdMax, s);
+    if (rc != ASTROZ_OK) return rc;
+    Launch L;
+    L.tileCount = c->cat.sgp4Tiles_count();
+    L.nt = n_times;
+    rc = queue_grid(c, L, n_times, nullptr, nullptr, nullptr, ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR,
+                    out_num_sats, out_sat_offset, s, true, &gt);
     c->timed = (rc == ASTROZ_OK);
     return rc;
 }

@@ -52,17 +52,26 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// output stage shared by K1 / K2: frame conversion + store
+// output stage shared by K1 / K2: frame conversion, then either
+//   * satellite-major: a warp's 32 consecutive epochs form one contiguous 768-byte run of the block;
+//     the 32 x (x,y,z) records are transposed through shared memory and leave as 128-bit stores --
+//     to local HBM, to the NVLS multicast address (multimem.st: one store, the switch replicates it to
+//     every GPU of the box) or to each peer mapping (fused all-gather over NVLink 5);
+//   * time-major: 24-byte records at stride n_sats*24 B, stored directly (L2 merges neighbours).
 // ---------------------------------------------------------------------------------------------------
-template <int kLayout, int kMode, bool kVel>
-__device__ __forceinline__ void store_cell(const GridArgs &a, uint32_t row, uint32_t t, CellOut &o) {
+template <int kMode, bool kVel>
+__device__ __forceinline__ void to_output_frame(const GridArgs &a, uint32_t t, CellOut &o) {
     if (kMode != 0) {
         const double sg = __ldg(a.gsin + t), cg = __ldg(a.gcos + t);
         eci_to_ecef(o.rx, o.ry, sg, cg);
         if (kVel) eci_to_ecef(o.vx, o.vy, sg, cg);  // pure rotation, no omega x r (src/Constellation.zig:501-506)
         if (kMode == 2) ecef_to_geodetic(o.rx, o.ry, o.rz);
     }
-    const size_t idx = (kLayout == 0) ? ((size_t)row * a.nTimes + t) * 3 : ((size_t)t * a.outNumSats + row) * 3;
+}
+
+template <bool kVel>
+__device__ __forceinline__ void store_time_major(const GridArgs &a, uint32_t row, uint32_t t, const CellOut &o) {
+    const size_t idx = ((size_t)t * a.outNumSats + row) * 3;
     double *p = a.pos + idx;
     __stcs(p, o.rx);
     __stcs(p + 1, o.ry);
@@ -75,12 +84,75 @@ __device__ __forceinline__ void store_cell(const GridArgs &a, uint32_t row, uint
     }
 }
 
+__device__ __forceinline__ void st_multimem_16(double *mc, double2 v) {
+    // 16 bytes to the multicast address: NVSwitch delivers the write to every GPU mapped by the object
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(__double2loint(v.x)),
+                 "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)), "r"(__double2hiint(v.y))
+                 : "memory");
+}
+__device__ __forceinline__ void st_multimem_8(double *mc, double v) {
+    asm volatile("multimem.st.weak.global.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+}
+
+constexpr int kStageDoubles = 32 * 3;  // one warp-run of positions (or velocities)
+
+// Emit one warp-run: epochs [tw, tw+32) of output row `row`.  All 32 lanes must call this; `valid`
+// masks lanes past the end of the time axis.  stage = this warp's 2 * kStageDoubles scratch.
+template <bool kVel, int kGather>
+__device__ __forceinline__ void emit_run_sat_major(const GridArgs &a, uint32_t row, uint32_t tw, uint32_t count,
+                                                   int lane, bool valid, const CellOut &o, double *stage) {
+    if (valid) {
+        stage[lane * 3 + 0] = o.rx;
+        stage[lane * 3 + 1] = o.ry;
+        stage[lane * 3 + 2] = o.rz;
+        if (kVel) {
+            stage[kStageDoubles + lane * 3 + 0] = o.vx;
+            stage[kStageDoubles + lane * 3 + 1] = o.vy;
+            stage[kStageDoubles + lane * 3 + 2] = o.vz;
+        }
+    }
+    __syncwarp();
+    const size_t base = ((size_t)row * a.nTimes + tw) * 3;  // in doubles; src/Constellation.zig:46-51
+    const bool vec = (count == 32) && ((base & 1) == 0);   // 16-byte aligned full run
+#pragma unroll
+    for (int which = 0; which < (kVel ? 2 : 1); ++which) {
+        const double *src = stage + which * kStageDoubles;
+        if (vec) {
+#pragma unroll
+            for (int c = lane; c < kStageDoubles / 2; c += 32) {
+                const double2 v = *reinterpret_cast<const double2 *>(src + 2 * c);
+                if (kGather == 1) {
+                    st_multimem_16((which ? a.mcVel : a.mcPos) + base + 2 * c, v);
+                } else if (kGather == 2) {
+                    for (int p = 0; p < a.nPeers; ++p)
+                        __stcs(reinterpret_cast<double2 *>((which ? a.peerVel[p] : a.peerPos[p]) + base + 2 * c), v);
+                } else {
+                    __stcs(reinterpret_cast<double2 *>((which ? a.vel : a.pos) + base + 2 * c), v);
+                }
+            }
+        } else {  // ragged tail or odd alignment: 8-byte stores
+            for (uint32_t i = lane; i < count * 3; i += 32) {
+                const double v = src[i];
+                if (kGather == 0) {
+                    __stcs((which ? a.vel : a.pos) + base + i, v);
+                } else if (kGather == 1) {
+                    st_multimem_8((which ? a.mcVel : a.mcPos) + base + i, v);
+                } else {
+                    for (int p = 0; p < a.nPeers; ++p) __stcs((which ? a.peerVel[p] : a.peerPos[p]) + base + i, v);
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K1: near-earth grid
 // ---------------------------------------------------------------------------------------------------
-template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes>
+template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes, int kGather>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(const GridArgs a) {
     __shared__ __align__(128) double tile[kSgp4TileDoubles];
+    __shared__ __align__(16) double stageAll[kLayout == 0 ? kWarps * 2 * kStageDoubles : 2];
     __shared__ __align__(8) uint64_t bar;
 
     const uint32_t tileIdx = blockIdx.x;
@@ -96,6 +168,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t0 = blockIdx.y * kStripe;
     const uint32_t t1 = min(t0 + (uint32_t)kStripe, a.nTimes);
+    double *stage = stageAll + (kLayout == 0 ? warp * 2 * kStageDoubles : 0);
     mbar_wait(&bar, 0);
 
 #pragma unroll 1
@@ -106,22 +179,30 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
         auto col = [colBase](int i) { return colBase[i * kTileSats]; };
         const double toff = __ldg(a.toff + sat);
         const uint32_t row = __ldg(a.orig + sat);
-        // a thread owns kLanes epochs of this satellite, 32 apart, so each warp-level store still covers 32
-        // consecutive epochs (one contiguous 768-byte run of the satellite-major block)
+        // a thread owns kLanes epochs of this satellite, 32 apart, so each warp-run is 32 consecutive epochs
+        // (one contiguous 768-byte run of the satellite-major block).  The loop is warp-uniform.
 #pragma unroll 1
-        for (uint32_t t = t0 + lane; t < t1; t += 32 * kLanes) {
+        for (uint32_t tw = t0; tw < t1; tw += 32 * kLanes) {
             double ts[kLanes];
 #pragma unroll
             for (int k = 0; k < kLanes; ++k)
-                ts[k] = __ldg(a.tbase + min(t + 32u * k, t1 - 1)) + toff;  // src/Constellation.zig:425
+                ts[k] = __ldg(a.tbase + min(tw + 32u * k + lane, t1 - 1)) + toff;  // src/Constellation.zig:425
             CellOut o[kLanes];
             sgp4_cell<kLanes>(col, ts, a.g, o);
 #pragma unroll
             for (int k = 0; k < kLanes; ++k) {
-                const uint32_t tk = t + 32u * k;
-                if (k == 0 || tk < t1) {
+                const uint32_t twk = tw + 32u * k;
+                if (twk >= t1) break;  // warp-uniform
+                const uint32_t tk = twk + lane;
+                const bool valid = tk < t1;
+                if (valid) {
                     if (a.status) a.status[(size_t)row * a.nTimes + tk] = (o[k].mrt < 1.0) ? 1 : 0;
-                    store_cell<kLayout, kMode, kVel>(a, row, tk, o[k]);
+                    to_output_frame<kMode, kVel>(a, tk, o[k]);
+                }
+                if (kLayout == 0) {
+                    emit_run_sat_major<kVel, kGather>(a, row, twk, min(32u, t1 - twk), lane, valid, o[k], stage);
+                } else if (valid) {
+                    store_time_major<kVel>(a, row, tk, o[k]);
                 }
             }
         }
@@ -143,13 +224,14 @@ static const Sgp4Variant kVariants[] = {
 int sgp4_variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const char *sgp4_variant_name(int v) { return (v >= 0 && v < sgp4_variant_count()) ? kVariants[v].name : "?"; }
 
-template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes>
+template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes, int kGather = 0>
 static cudaError_t launch_k1(const GridArgs &a, cudaStream_t stream) {
     const uint32_t tiles = (a.nSats + kTileSats - 1) / kTileSats;
     const uint32_t stripes = (a.nTimes + kStripe - 1) / kStripe;
     if (tiles == 0 || stripes == 0) return cudaSuccess;
     dim3 grid(tiles, stripes);
-    sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks, kLanes><<<grid, kWarps * 32, 0, stream>>>(a);
+    sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks, kLanes, kGather>
+        <<<grid, kWarps * 32, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -183,6 +265,13 @@ static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int
 }
 
 cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant) {
+    if (a.gather != 0) {  // fused all-gather: satellite-major TEME only
+        if (layout != 0 || mode != 0) return cudaErrorInvalidValue;
+        const bool gv = (a.gather == 1 ? a.mcVel : a.peerVel[0]) != nullptr;
+        if (a.gather == 1) return gv ? launch_k1<0, 0, true, AZ_DEFAULT_K1, 1>(a, stream)
+                                     : launch_k1<0, 0, false, AZ_DEFAULT_K1, 1>(a, stream);
+        return gv ? launch_k1<0, 0, true, AZ_DEFAULT_K1, 2>(a, stream) : launch_k1<0, 0, false, AZ_DEFAULT_K1, 2>(a, stream);
+    }
     const bool vel = a.vel != nullptr;
 #define AZ_K1(L, M)                                                               \
     if (layout == L && mode == M)                                                 \
@@ -230,9 +319,10 @@ cudaError_t launch_sdp4_lattice(const Sdp4Sat *sats, uint32_t nSats, double2 *la
 constexpr int kSdp4Threads = 128;
 constexpr int kSdp4Stripe = 512;
 
-template <int kLayout, int kMode, bool kVel>
+template <int kLayout, int kMode, bool kVel, int kGather>
 __global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridArgs a) {
     __shared__ Sdp4Sat e;
+    __shared__ __align__(16) double stageAll[kLayout == 0 ? (kSdp4Threads / 32) * 2 * kStageDoubles : 2];
     const uint32_t sat = blockIdx.x;
     {
         const double *src = reinterpret_cast<const double *>(a.sdp4 + sat);
@@ -240,13 +330,18 @@ __global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridAr
         for (int i = threadIdx.x; i < (int)(sizeof(Sdp4Sat) / 8); i += kSdp4Threads) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *stage = stageAll + (kLayout == 0 ? warp * 2 * kStageDoubles : 0);
     const uint32_t row = __ldg(a.orig + sat);
     const uint32_t t0 = blockIdx.y * kSdp4Stripe;
     const uint32_t t1 = min(t0 + (uint32_t)kSdp4Stripe, a.nTimes);
 #pragma unroll 1
-    for (uint32_t t = t0 + threadIdx.x; t < t1; t += kSdp4Threads) {
-        const double ts = a.tsince ? __ldg(a.tsince + t)
-                                   : (__ldg(a.jdFull + t) - e.epochJd) * 1440.0;  // src/Constellation.zig:465
+    for (uint32_t tw = t0 + warp * 32; tw < t1; tw += kSdp4Threads) {  // warp-uniform
+        const uint32_t t = tw + lane;
+        const bool valid = t < t1;
+        const uint32_t tc = min(t, t1 - 1);
+        const double ts = a.tsince ? __ldg(a.tsince + tc)
+                                   : (__ldg(a.jdFull + tc) - e.epochJd) * 1440.0;  // src/Constellation.zig:465
         double xli = e.xlamo, xni = e.no, atime = 0.0;
         if (e.irez != 0) {
             const int node = resonance_node(ts);
@@ -260,27 +355,36 @@ __global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridAr
         }
         CellOut o;
         const int st = sdp4_cell(e, ts, xli, xni, atime, a.g, o);
-        if (a.status) a.status[(size_t)row * a.nTimes + t] = (uint8_t)st;
+        if (valid && a.status) a.status[(size_t)row * a.nTimes + t] = (uint8_t)st;
         if (st != 0) {  // zero fill, per satellite (src/Constellation.zig:468-471,511-528 does it per batch of 8)
-            const size_t idx = (kLayout == 0) ? ((size_t)row * a.nTimes + t) * 3 : ((size_t)t * a.outNumSats + row) * 3;
-            a.pos[idx] = a.pos[idx + 1] = a.pos[idx + 2] = 0.0;
-            if (kVel) a.vel[idx] = a.vel[idx + 1] = a.vel[idx + 2] = 0.0;
-        } else {
-            store_cell<kLayout, kMode, kVel>(a, row, t, o);
+            o.rx = o.ry = o.rz = o.vx = o.vy = o.vz = 0.0;
+        } else if (valid) {
+            to_output_frame<kMode, kVel>(a, t, o);
+        }
+        if (kLayout == 0) {
+            emit_run_sat_major<kVel, kGather>(a, row, tw, min(32u, t1 - tw), lane, valid, o, stage);
+        } else if (valid) {
+            store_time_major<kVel>(a, row, t, o);
         }
     }
 }
 
-template <int kLayout, int kMode, bool kVel>
+template <int kLayout, int kMode, bool kVel, int kGather = 0>
 static cudaError_t launch_k2(const GridArgs &a, cudaStream_t stream) {
     const uint32_t stripes = (a.nTimes + kSdp4Stripe - 1) / kSdp4Stripe;
     if (a.nSats == 0 || stripes == 0) return cudaSuccess;
     dim3 grid(a.nSats, stripes);
-    sdp4_grid_kernel<kLayout, kMode, kVel><<<grid, kSdp4Threads, 0, stream>>>(a);
+    sdp4_grid_kernel<kLayout, kMode, kVel, kGather><<<grid, kSdp4Threads, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_sdp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream) {
+    if (a.gather != 0) {
+        if (layout != 0 || mode != 0) return cudaErrorInvalidValue;
+        const bool gv = (a.gather == 1 ? a.mcVel : a.peerVel[0]) != nullptr;
+        if (a.gather == 1) return gv ? launch_k2<0, 0, true, 1>(a, stream) : launch_k2<0, 0, false, 1>(a, stream);
+        return gv ? launch_k2<0, 0, true, 2>(a, stream) : launch_k2<0, 0, false, 2>(a, stream);
+    }
     const bool vel = a.vel != nullptr;
 #define AZ_K2(L, M) \
     if (layout == L && mode == M) return vel ? launch_k2<L, M, true>(a, stream) : launch_k2<L, M, false>(a, stream);

@@ -30,8 +30,19 @@ struct GridArgs {
     double *vel = nullptr;               // nullable
     uint8_t *status = nullptr;           // nullable, [outRow][nTimes]
     uint32_t outNumSats = 0;             // row count of the output block (time-major stride)
+    // fused all-gather (satellite-major only): when gather != 0 the result block is written to every GPU
+    // of the box from inside the kernel -- gather 1: one multimem.st per 16 bytes to the NVLS multicast
+    // mapping of the symmetric buffer (mcPos/mcVel); gather 2: plain stores to each peer mapping.
+    int gather = 0;
+    int nPeers = 0;
+    double *mcPos = nullptr;
+    double *mcVel = nullptr;
+    double *peerPos[8] = {};
+    double *peerVel[8] = {};
     GravConsts g{};
 };
+
+constexpr int kMaxPeers = 8;
 
 // K1: near-earth grid.  variant selects a tuning configuration (0 = default).
 cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant);

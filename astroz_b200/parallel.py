@@ -91,3 +91,49 @@ class ShardedPropagator:
             return
         mine = full_block[self.rank * self.rows:(self.rank + 1) * self.rows]
         self.dist.all_gather_into_tensor(full_block, mine)
+
+
+class SymmetricBlock:
+    """The whole (padded_rows, n_times, 3) position and velocity blocks in NVLink-symmetric memory
+    (torch.distributed._symmetric_memory): every rank allocates the same buffer, rendezvous maps all
+    peers' copies (and, where NVLS is available, one multicast address) into this process.  The fused
+    kernels write each rank's rows into every copy, so after `barrier()` all ranks hold the whole block."""
+
+    def __init__(self, padded_rows: int, n_times: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.torch = torch
+        group = group if group is not None else dist.group.WORLD
+        self.block = symm_mem.empty((2, padded_rows, n_times, 3), dtype=torch.float64, device=device)
+        name = group.group_name if hasattr(group, "group_name") else group
+        self.handle = symm_mem.rendezvous(self.block, name)
+        self.pos, self.vel = self.block[0], self.block[1]
+        vel_off = self.block[1].data_ptr() - self.block[0].data_ptr()
+        self.peer_pos = [int(p) for p in self.handle.buffer_ptrs]
+        self.peer_vel = [int(p) + vel_off for p in self.handle.buffer_ptrs]
+        mc = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.mc_pos = mc
+        self.mc_vel = mc + vel_off if mc else 0
+
+    @property
+    def has_multicast(self) -> bool:
+        return self.mc_pos != 0
+
+    def barrier(self) -> None:
+        self.handle.barrier(channel=0)
+
+
+def propagate_gather(sp: ShardedPropagator, sym: SymmetricBlock, jd, fr, velocities: bool = True, stream: int = 0,
+                     use_multicast: bool = True) -> None:
+    """One fused launch per rank: propagate this rank's satellites and deliver the rows to every GPU
+    (multimem.st through the NVSwitch when multicast is mapped, peer stores otherwise)."""
+    if sp.local is None:
+        return
+    if use_multicast and sym.has_multicast:
+        sp.local.propagate_gather(jd, fr, mc_pos=sym.mc_pos, mc_vel=sym.mc_vel if velocities else 0,
+                                  out_num_sats=sp.padded_rows, out_sat_offset=sp.rank * sp.rows, stream=stream)
+    else:
+        sp.local.propagate_gather(jd, fr, peer_pos=sym.peer_pos, peer_vel=sym.peer_vel if velocities else None,
+                                  out_num_sats=sp.padded_rows, out_sat_offset=sp.rank * sp.rows, stream=stream)

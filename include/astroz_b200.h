@@ -110,6 +110,21 @@ int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, con
                                                    int32_t mode, int32_t layout, uint32_t out_num_sats,
                                                    uint32_t out_sat_offset, void *stream);
 
+/* Fused propagate + all-gather for satellite-sharded multi-GPU runs (no reference
+ * counterpart -- the reference is single-process).  TEME, satellite-major.  This handle's rows
+ * [out_sat_offset, out_sat_offset + n) of the (out_num_sats, n_times, 3) block are written, from inside the
+ * propagation kernels, into EVERY GPU's copy of the block:
+ *   mc_pos / mc_vel != NULL : NVLS multicast mappings of a symmetric allocation -- one multimem.st per
+ *                             16 bytes, NVSwitch replicates it to all GPUs (this one included);
+ *   otherwise               : peer_pos[0..n_peers) / peer_vel[...] are the per-GPU mappings of the block
+ *                             (this GPU's own mapping included) and each run is stored to all of them.
+ * peer_vel / mc_vel may be NULL (positions only).  Asynchronous on `stream`; the caller synchronises the
+ * ranks (e.g. a symmetric-memory barrier) before reading other ranks' rows. */
+int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, const double *jd, const double *fr,
+                                                   uint32_t n_times, void *const *peer_pos, void *const *peer_vel,
+                                                   uint32_t n_peers, void *mc_pos, void *mc_vel,
+                                                   uint32_t out_num_sats, uint32_t out_sat_offset, void *stream);
+
 /* Constellation.resetCarry (src/Constellation.zig:214-218).  The device path re-derives the SDP4
  * resonance state from a 720-minute lattice on every call, so this is a semantic no-op kept for drop-in use. */
 int32_t astroz_cuda_constellation_reset_carry(astroz_constellation_t h);
