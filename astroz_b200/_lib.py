@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         "astroz_cuda_constellation_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "astroz_cuda_sgp4_propagate_into": (i32, [vp, dp, u32, dp, dp, dp, i32, C.c_double, i32]),
         "astroz_cuda_sgp4_propagate_into_device": (i32, [vp, dp, u32, dp, vp, vp, i32, C.c_double, i32, vp]),
+        "astroz_cuda_sgp4_screen": (i32, [vp, dp, u32, dp, u32, C.c_double, C.c_double, dp, C.POINTER(u32)]),
         "astroz_cuda_sgp4_init": (i32, [C.c_char_p, C.c_char_p, i32, i32, C.POINTER(vp)]),
         "astroz_cuda_sgp4_free": (None, [vp]),
         "astroz_cuda_sgp4_is_deep_space": (i32, [vp]),
@@ -99,7 +100,8 @@ EXPORTS = [
     "astroz_cuda_constellation_propagate_device", "astroz_cuda_constellation_propagate_gather",
     "astroz_cuda_constellation_reset_carry",
     "astroz_cuda_constellation_synchronize", "astroz_cuda_constellation_last_kernel_ms",
-    "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sgp4_init",
+    "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sgp4_screen",
+    "astroz_cuda_sgp4_init",
     "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch",
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_fp64_peak",
 ]

@@ -200,6 +200,22 @@ class Constellation:
         return positions, velocities
 
 
+    def screen_conjunction(self, times, target: int, threshold: float = 10.0, epoch_offsets=None,
+                           reference_jd: float = 0.0):
+        """Sgp4Constellation.screen_conjunction(times, target, threshold, epoch_offsets=, reference_jd=)
+        -> (min_distances[n_sgp4] km, min_t_indices[n_sgp4] uint32): fused propagate + single-target screen
+        (src/Constellation.zig:683-756).  Nothing but the 12 bytes per satellite leaves the GPU."""
+        times = as_f64(times)
+        ns = self.numSgp4
+        off = np.zeros(ns) if epoch_offsets is None else as_f64(epoch_offsets)[:ns].copy()
+        dist = np.empty(ns)
+        tidx = np.empty(ns, dtype=np.uint32)
+        check(lib().astroz_cuda_sgp4_screen(self._h, dptr(times), times.shape[0], dptr(off), int(target),
+                                            float(threshold), float(reference_jd), dptr(dist),
+                                            tidx.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return dist, tidx
+
+
 def fp64_peak_tflops(device: int = 0) -> float:
     """Measured DFMA throughput of the device (the fp64 roofline denominator)."""
     v = C.c_double()

@@ -657,6 +657,62 @@ int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *
     return ASTROZ_OK;
 }
 
+int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                const double *epoch_offsets, uint32_t target_idx, double threshold,
+                                double reference_jd, double *out_min_dists, uint32_t *out_min_t) {
+    (void)reference_jd;
+    Constellation *c = static_cast<Constellation *>(h);
+    if (!c || !times || !epoch_offsets || !out_min_dists || !out_min_t) return ASTROZ_NULL_POINTER;
+    const uint32_t ns = c->cat.nSgp4;
+    if (ns == 0 || n_times == 0) return ASTROZ_OK;
+    if (target_idx >= ns) {
+        g_lastError = "target index out of range";
+        return ASTROZ_VALUE_ERROR;
+    }
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    const uint32_t padded = c->cat.sgp4Padded();
+    int32_t rc = reserve_time(c, n_times);
+    if (rc != ASTROZ_OK) return rc;
+    for (uint32_t t = 0; t < n_times; ++t) c->hTime[t] = times[t];
+    AZ_CUDA(cudaMemcpyAsync(c->dTime.p, c->hTime, (size_t)n_times * 8, cudaMemcpyHostToDevice, s));
+    if (padded > c->hToffCap) {
+        if (c->hToffCall) cudaFreeHost(c->hToffCall);
+        c->hToffCall = nullptr;
+        AZ_CUDA(cudaMallocHost(&c->hToffCall, (size_t)padded * 8));
+        c->hToffCap = padded;
+    }
+    for (uint32_t i = 0; i < padded; ++i) c->hToffCall[i] = epoch_offsets[std::min(i, ns - 1)];
+    AZ_CUDA(c->dToffCall.reserve(padded));
+    AZ_CUDA(cudaMemcpyAsync(c->dToffCall.p, c->hToffCall, (size_t)padded * 8, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaEventRecord(c->timeCopied, s));
+    c->timePending = true;
+    // scratch: target track [nt][3] | minDist [ns] | minT [ns] (as doubles' worth of space)
+    AZ_CUDA(c->dPos.reserve((size_t)n_times * 3 + 2 * (size_t)ns + 2));
+    az::ScreenArgs a;
+    a.sgp4Tiles = c->dTiles.p;
+    a.toff = c->dToffCall.p;
+    a.tbase = c->dTime.p;
+    a.nSats = ns;
+    a.nTimes = n_times;
+    a.targetIdx = target_idx;
+    a.thresholdSq = threshold * threshold;
+    a.track = c->dPos.p;
+    a.minDist = c->dPos.p + (size_t)n_times * 3;
+    a.minT = reinterpret_cast<uint32_t *>(a.minDist + ns);
+    a.g = c->g;
+    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    AZ_CUDA(az::launch_sgp4_screen(a, s));
+    AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = true;
+    AZ_CUDA(cudaMemcpyAsync(out_min_dists, a.minDist, (size_t)ns * 8, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(out_min_t, a.minT, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return ASTROZ_OK;
+}
+
 // ---- single satellite ----------------------------------------------------------------------------
 int32_t astroz_cuda_sgp4_init(const char *line1, const char *line2, int32_t grav, int32_t device, astroz_sgp4_t *out) {
     if (!line1 || !line2 || !out) return ASTROZ_NULL_POINTER;

@@ -53,11 +53,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
 
 // ---------------------------------------------------------------------------------------------------
 // output stage shared by K1 / K2: frame conversion, then either
-//   * satellite-major: a warp's 32 consecutive epochs form one contiguous 768-byte run of the block;
-//     the 32 x (x,y,z) records are transposed through shared memory and leave as 128-bit stores --
-//     to local HBM, to the NVLS multicast address (multimem.st: one store, the switch replicates it to
-//     every GPU of the box) or to each peer mapping (fused all-gather over NVLink 5);
-//   * time-major: 24-byte records at stride n_sats*24 B, stored directly (L2 merges neighbours).
+//   * local block (either layout): each lane stores its 24-byte records directly (streaming stores; the
+//     L2 merges the column stores of a warp-run into full lines before they reach HBM);
+//   * fused all-gather (satellite-major): a warp's 32 consecutive epochs form one contiguous 768-byte
+//     run; the 32 x (x,y,z) records are transposed through shared memory and leave as 128-bit stores to
+//     each peer mapping over NVLink 5, or as one multimem.st to the NVLS multicast address.
 // ---------------------------------------------------------------------------------------------------
 template <int kMode, bool kVel>
 __device__ __forceinline__ void to_output_frame(const GridArgs &a, uint32_t t, CellOut &o) {
@@ -69,9 +69,12 @@ __device__ __forceinline__ void to_output_frame(const GridArgs &a, uint32_t t, C
     }
 }
 
-template <bool kVel>
-__device__ __forceinline__ void store_time_major(const GridArgs &a, uint32_t row, uint32_t t, const CellOut &o) {
-    const size_t idx = ((size_t)t * a.outNumSats + row) * 3;
+// direct 24-byte record stores; idx in doubles.  For the local satellite-major block this measured ~4 %
+// faster than staging through shared memory (the L2 merges the three 8-byte column stores of a warp-run),
+// so the staged 128-bit path is used only where every byte crosses NVLink (fused all-gather).
+template <int kLayout, bool kVel>
+__device__ __forceinline__ void store_direct(const GridArgs &a, uint32_t row, uint32_t t, const CellOut &o) {
+    const size_t idx = (kLayout == 0) ? ((size_t)row * a.nTimes + t) * 3 : ((size_t)t * a.outNumSats + row) * 3;
     double *p = a.pos + idx;
     __stcs(p, o.rx);
     __stcs(p + 1, o.ry);
@@ -152,7 +155,7 @@ __device__ __forceinline__ void emit_run_sat_major(const GridArgs &a, uint32_t r
 template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes, int kGather>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(const GridArgs a) {
     __shared__ __align__(128) double tile[kSgp4TileDoubles];
-    __shared__ __align__(16) double stageAll[kLayout == 0 ? kWarps * 2 * kStageDoubles : 2];
+    __shared__ __align__(16) double stageAll[kGather != 0 ? kWarps * 2 * kStageDoubles : 2];
     __shared__ __align__(8) uint64_t bar;
 
     const uint32_t tileIdx = blockIdx.x;
@@ -168,8 +171,73 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t t0 = blockIdx.y * kStripe;
     const uint32_t t1 = min(t0 + (uint32_t)kStripe, a.nTimes);
-    double *stage = stageAll + (kLayout == 0 ? warp * 2 * kStageDoubles : 0);
+    double *stage = stageAll + (kGather != 0 ? warp * 2 * kStageDoubles : 0);
     mbar_wait(&bar, 0);
+
+    if constexpr (kLayout == 1 && kGather == 0) {
+        // ---- time-major: for one epoch the tile's 8 satellites are 192 contiguous bytes of the block
+        // (when their output rows are consecutive, i.e. an all-near-earth catalog).  Records are transposed
+        // through shared memory -- [epoch][sat][xyz] -- and leave as 128-bit stores; per-lane 24-byte stores
+        // at a stride of n_sats*24 B measured 2.6x slower with velocities on.
+        constexpr int kRun = 32 * kLanes;
+        __shared__ __align__(16) double tpos[kRun * kTileSats * 3];
+        __shared__ __align__(16) double tvel[kVel ? kRun * kTileSats * 3 : 2];
+        const uint32_t sat0 = tileIdx * kTileSats;
+        const uint32_t row0 = __ldg(a.orig + sat0);
+        const uint32_t nReal = min((uint32_t)kTileSats, a.nSats - sat0);
+        bool block8 = nReal == kTileSats && ((((size_t)a.outNumSats * 3) & 1) == 0) && ((row0 * 3u) & 1u) == 0;
+#pragma unroll
+        for (int k = 1; k < kTileSats; ++k) block8 = block8 && (k >= (int)nReal || __ldg(a.orig + sat0 + k) == row0 + k);
+#pragma unroll 1
+        for (uint32_t tw = t0; tw < t1; tw += kRun) {
+#pragma unroll 1
+            for (int sl = warp; sl < (int)nReal; sl += kWarps) {
+                const uint32_t sat = sat0 + sl;
+                const double *colBase = tile + sl;
+                auto col = [colBase](int i) { return colBase[i * kTileSats]; };
+                const double toff = __ldg(a.toff + sat);
+                const uint32_t row = __ldg(a.orig + sat);
+                double ts[kLanes];
+#pragma unroll
+                for (int k = 0; k < kLanes; ++k) ts[k] = __ldg(a.tbase + min(tw + 32u * k + lane, t1 - 1)) + toff;
+                CellOut o[kLanes];
+                sgp4_cell<kLanes>(col, ts, a.g, o);
+#pragma unroll
+                for (int k = 0; k < kLanes; ++k) {
+                    const uint32_t tk = tw + 32u * k + lane;
+                    if (tk >= t1) continue;
+                    if (a.status) a.status[(size_t)row * a.nTimes + tk] = (o[k].mrt < 1.0) ? 1 : 0;
+                    to_output_frame<kMode, kVel>(a, tk, o[k]);
+                    if (block8) {
+                        double *p = tpos + ((32 * k + lane) * kTileSats + sl) * 3;
+                        p[0] = o[k].rx; p[1] = o[k].ry; p[2] = o[k].rz;
+                        if (kVel) {
+                            double *v = tvel + ((32 * k + lane) * kTileSats + sl) * 3;
+                            v[0] = o[k].vx; v[1] = o[k].vy; v[2] = o[k].vz;
+                        }
+                    } else {
+                        store_direct<1, kVel>(a, row, tk, o[k]);
+                    }
+                }
+            }
+            if (block8) {  // CTA-uniform
+                __syncthreads();
+                const uint32_t count = min((uint32_t)kRun, t1 - tw);           // epochs in this run
+                constexpr int kChunks = kTileSats * 3 / 2;                      // 16-byte chunks per epoch row
+                for (uint32_t i = threadIdx.x; i < count * kChunks; i += kWarps * 32) {
+                    const uint32_t j = i / kChunks, ch = i % kChunks;
+                    const size_t dst = ((size_t)(tw + j) * a.outNumSats + row0) * 3 + 2 * ch;
+                    __stcs(reinterpret_cast<double2 *>(a.pos + dst),
+                           *reinterpret_cast<const double2 *>(tpos + j * kTileSats * 3 + 2 * ch));
+                    if (kVel)
+                        __stcs(reinterpret_cast<double2 *>(a.vel + dst),
+                               *reinterpret_cast<const double2 *>(tvel + j * kTileSats * 3 + 2 * ch));
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
 
 #pragma unroll 1
     for (int sl = warp; sl < kTileSats; sl += kWarps) {
@@ -199,10 +267,10 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
                     if (a.status) a.status[(size_t)row * a.nTimes + tk] = (o[k].mrt < 1.0) ? 1 : 0;
                     to_output_frame<kMode, kVel>(a, tk, o[k]);
                 }
-                if (kLayout == 0) {
+                if (kGather != 0) {
                     emit_run_sat_major<kVel, kGather>(a, row, twk, min(32u, t1 - twk), lane, valid, o[k], stage);
                 } else if (valid) {
-                    store_time_major<kVel>(a, row, tk, o[k]);
+                    store_direct<kLayout, kVel>(a, row, tk, o[k]);
                 }
             }
         }
@@ -322,7 +390,7 @@ constexpr int kSdp4Stripe = 512;
 template <int kLayout, int kMode, bool kVel, int kGather>
 __global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridArgs a) {
     __shared__ Sdp4Sat e;
-    __shared__ __align__(16) double stageAll[kLayout == 0 ? (kSdp4Threads / 32) * 2 * kStageDoubles : 2];
+    __shared__ __align__(16) double stageAll[kGather != 0 ? (kSdp4Threads / 32) * 2 * kStageDoubles : 2];
     const uint32_t sat = blockIdx.x;
     {
         const double *src = reinterpret_cast<const double *>(a.sdp4 + sat);
@@ -331,7 +399,7 @@ __global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridAr
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *stage = stageAll + (kLayout == 0 ? warp * 2 * kStageDoubles : 0);
+    double *stage = stageAll + (kGather != 0 ? warp * 2 * kStageDoubles : 0);
     const uint32_t row = __ldg(a.orig + sat);
     const uint32_t t0 = blockIdx.y * kSdp4Stripe;
     const uint32_t t1 = min(t0 + (uint32_t)kSdp4Stripe, a.nTimes);
@@ -361,10 +429,10 @@ __global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridAr
         } else if (valid) {
             to_output_frame<kMode, kVel>(a, t, o);
         }
-        if (kLayout == 0) {
+        if (kGather != 0) {
             emit_run_sat_major<kVel, kGather>(a, row, tw, min(32u, t1 - tw), lane, valid, o, stage);
         } else if (valid) {
-            store_time_major<kVel>(a, row, t, o);
+            store_direct<kLayout, kVel>(a, row, t, o);
         }
     }
 }
@@ -391,6 +459,103 @@ cudaError_t launch_sdp4_grid(const GridArgs &a, int mode, int layout, cudaStream
     AZ_K2(0, 0) AZ_K2(0, 1) AZ_K2(0, 2) AZ_K2(1, 0) AZ_K2(1, 1) AZ_K2(1, 2)
 #undef AZ_K2
     return cudaErrorInvalidValue;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: fused propagate + single-target screen (src/Constellation.zig:683-756).  Pass 1 propagates the
+// target over the whole time axis (n_times cells).  Pass 2 is the K1 cell core with the store stage
+// replaced by a running (min distance^2, first epoch index) per satellite: a warp owns one satellite
+// over ALL epochs, reduces with shuffles and writes 12 bytes -- the 48 B/cell result block never exists.
+// The reference rotates both vectors to ECEF with the same GMST first (:724,739); a common rotation
+// leaves the distance unchanged, so it is skipped.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) sgp4_track_kernel(const ScreenArgs a) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nTimes) return;
+    const double *tile = a.sgp4Tiles + (size_t)(a.targetIdx / kTileSats) * kSgp4TileDoubles + (a.targetIdx % kTileSats);
+    auto col = [tile](int i) { return __ldg(tile + i * kTileSats); };
+    const double ts[1] = {__ldg(a.tbase + t) + __ldg(a.toff + a.targetIdx)};
+    CellOut o[1];
+    sgp4_cell<1>(col, ts, a.g, o);
+    a.track[(size_t)t * 3 + 0] = o[0].rx;
+    a.track[(size_t)t * 3 + 1] = o[0].ry;
+    a.track[(size_t)t * 3 + 2] = o[0].rz;
+}
+
+constexpr int kScreenWarps = 4;
+constexpr int kScreenLanes = 2;
+
+__global__ void __launch_bounds__(kScreenWarps * 32, 3) sgp4_screen_kernel(const ScreenArgs a) {
+    __shared__ __align__(128) double tile[kSgp4TileDoubles];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tileIdx = blockIdx.x;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, kSgp4TileBytes);
+        tma_bulk_g2s(tile, a.sgp4Tiles + (size_t)tileIdx * kSgp4TileDoubles, kSgp4TileBytes, &bar);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    mbar_wait(&bar, 0);
+#pragma unroll 1
+    for (int sl = warp; sl < kTileSats; sl += kScreenWarps) {
+        const uint32_t sat = tileIdx * kTileSats + sl;
+        if (sat >= a.nSats) break;
+        const double *colBase = tile + sl;
+        auto col = [colBase](int i) { return colBase[i * kTileSats]; };
+        const double toff = __ldg(a.toff + sat);
+        double best = a.thresholdSq;   // src/Constellation.zig:703-706: start at threshold^2, index 0
+        uint32_t bestT = 0;
+        if (sat != a.targetIdx) {
+#pragma unroll 1
+            for (uint32_t tw = 0; tw < a.nTimes; tw += 32 * kScreenLanes) {
+                double ts[kScreenLanes];
+                uint32_t tk[kScreenLanes];
+#pragma unroll
+                for (int k = 0; k < kScreenLanes; ++k) {
+                    tk[k] = tw + 32u * k + lane;
+                    ts[k] = __ldg(a.tbase + min(tk[k], a.nTimes - 1)) + toff;
+                }
+                CellOut o[kScreenLanes];
+                sgp4_cell<kScreenLanes>(col, ts, a.g, o);
+#pragma unroll
+                for (int k = 0; k < kScreenLanes; ++k) {
+                    if (tk[k] < a.nTimes) {
+                        const double *tg = a.track + (size_t)tk[k] * 3;
+                        const double dx = __ldg(tg) - o[k].rx, dy = __ldg(tg + 1) - o[k].ry, dz = __ldg(tg + 2) - o[k].rz;
+                        const double d2 = fma(dx, dx, fma(dy, dy, dz * dz));
+                        if (d2 < best) {  // strict: the earliest epoch of the minimum wins (:745-748)
+                            best = d2;
+                            bestT = tk[k];
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+                const uint32_t ot = __shfl_xor_sync(0xffffffffu, bestT, off);
+                if (ob < best || (ob == best && ot < bestT)) {
+                    best = ob;
+                    bestT = ot;
+                }
+            }
+        }
+        if (lane == 0) {
+            a.minDist[sat] = sqrt(best);  // :753-755
+            a.minT[sat] = (best < a.thresholdSq) ? bestT : 0u;
+        }
+    }
+}
+
+cudaError_t launch_sgp4_screen(const ScreenArgs &a, cudaStream_t stream) {
+    if (a.nSats == 0 || a.nTimes == 0) return cudaSuccess;
+    sgp4_track_kernel<<<(a.nTimes + 127) / 128, 128, 0, stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const uint32_t tiles = (a.nSats + kTileSats - 1) / kTileSats;
+    sgp4_screen_kernel<<<tiles, kScreenWarps * 32, 0, stream>>>(a);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -50,6 +50,22 @@ cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream
 cudaError_t launch_sdp4_lattice(const Sdp4Sat *sats, uint32_t nSats, double2 *lattice, int nodes, cudaStream_t stream);
 // K2: deep-space grid.
 cudaError_t launch_sdp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream);
+// K3: fused propagate + single-target conjunction screen (src/Constellation.zig:683-756).  No position block
+// is written: per satellite the minimum distance to the target over all epochs (and its epoch index).
+struct ScreenArgs {
+    const double *sgp4Tiles = nullptr;
+    const double *toff = nullptr;     // per-satellite epoch offsets (padded)
+    const double *tbase = nullptr;    // times[n_times]
+    uint32_t nSats = 0, nTimes = 0;
+    uint32_t targetIdx = 0;
+    double thresholdSq = 0.0;
+    double *track = nullptr;          // scratch [n_times][3]: target positions
+    double *minDist = nullptr;        // out [nSats]
+    uint32_t *minT = nullptr;         // out [nSats]
+    GravConsts g{};
+};
+cudaError_t launch_sgp4_screen(const ScreenArgs &a, cudaStream_t stream);
+
 // DFMA throughput microbenchmark: returns achieved fp64 FLOP/s (FMA = 2).
 cudaError_t measure_fp64_peak(double *flops);
 

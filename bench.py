@@ -188,6 +188,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         import torch.distributed as dist
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
@@ -266,6 +268,23 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     e2e_value = cells * world / e2e_s
     h2d = 2 * nt * 8
     d2h = 2 * n * nt * 3 * 8
+
+    # ---- a device-resident consumer: fused propagate + single-target screen through the host API -----------
+    screen = None
+    if c.numSdp4 == 0:
+        times_min = ((jd + fr) - (jd[0] + fr[0])) * 1440.0
+        offs = ((jd[0] + fr[0]) - c.epochs) * 1440.0
+        for _ in range(2):
+            c.screen_conjunction(times_min, 0, 10.0, epoch_offsets=offs, reference_jd=float(jd[0] + fr[0]))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            dmin, tmin = c.screen_conjunction(times_min, 0, 10.0, epoch_offsets=offs, reference_jd=float(jd[0] + fr[0]))
+        scr_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+        screen = {"value": cells * world / scr_s, "unit": "props/s", "ms_per_call": scr_s * 1e3,
+                  "d2h_bytes_per_call": 12 * n, "api": "Constellation.screen_conjunction (src/Constellation.zig:683-756)",
+                  "note": "same cells propagated, minimum range to one target reduced on the device: host-to-host call "
+                          "not bound by PCIe"}
 
     # ---- the north star's collective, measured apart from `value` -------------------------------------
     # (a) baseline: shard-local kernel, then ONE ncclAllGather of the [pos|vel] block;
@@ -379,6 +398,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         "e2e": {"value": e2e_value, "unit": "props/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "d2h_GBs": d2h / e2e_s / 1e9,
                 "api": "Constellation.propagate(jd, fr, pos, vel) with pinned host buffers", "checksum": checksum},
+        "e2e_screen": screen,
         "gpu_launches": kernels_per_step * args.steps,
         "clocks": clocks,
         "roofline": roofline,

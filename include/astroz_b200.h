@@ -142,6 +142,18 @@ int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const d
                                                const double *epoch_offsets, double *d_pos, double *d_vel,
                                                int32_t mode, double reference_jd, int32_t layout, void *stream);
 
+/* Fused propagate + single-target conjunction screen: replaces Constellation.screenConstellation
+ * (src/Constellation.zig:683-756) as called by Sgp4Constellation.screen_conjunction
+ * (bindings/python/src/sgp4.zig).  Near-earth satellites only, tsince = times[t] + epoch_offsets[sat].
+ * out_min_dists[n_sgp4]: minimum distance (km) to satellite `target_idx` over all times, or `threshold`
+ * when never closer; out_min_t[n_sgp4]: index of the (first) time of that minimum, 0 when none.  The
+ * target's own entry stays (threshold, 0).  No position block is produced or copied: 12 bytes per
+ * satellite come back.  reference_jd is accepted for signature parity (a common GMST rotation does not
+ * change distances).  HOST buffers. */
+int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                const double *epoch_offsets, uint32_t target_idx, double threshold,
+                                double reference_jd, double *out_min_dists, uint32_t *out_min_t);
+
 /* block until everything queued on the handle's stream has finished */
 int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h);
 

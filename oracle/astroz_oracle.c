@@ -1134,3 +1134,38 @@ int azo_satrec_array_sgp4(const char *const *l1, const char *const *l2, size_t n
     }
     return 0;
 }
+
+int azo_screen_constellation(const char *const *l1, const char *const *l2, size_t n, int grav, const double *times,
+                             size_t nt, const double *epoch_offsets, size_t target_idx, double threshold,
+                             double reference_jd, double *outMinDists, uint32_t *outMinT) {
+    azo_sgp4 *el = (azo_sgp4 *)malloc(sizeof(azo_sgp4) * (n ? n : 1));
+    int rc = 0;
+    for (size_t i = 0; i < n; i++) {
+        azo_tle t;
+        if (azo_tle_parse(l1[i], l2[i], &t) != AZO_OK) { rc = AZO_BAD_TLE; goto done; }
+        rc = azo_sgp4_init(&t, grav, &el[i]);
+        if (rc != AZO_OK) goto done;
+    }
+    const double thresholdSq = threshold * threshold;            /* Constellation.zig:698 */
+    for (size_t i = 0; i < n; i++) { outMinDists[i] = thresholdSq; outMinT[i] = 0; } /* :703-706 */
+    for (size_t ti = 0; ti < nt; ti++) {                         /* :720-751 */
+        double g = azo_julian_to_gmst(reference_jd + times[ti] / 1440.0);
+        double sinG = sin(g), cosG = cos(g);
+        double r[3], v[3], tp[3];
+        azo_sgp4_propagate(&el[target_idx], times[ti] + epoch_offsets[target_idx], r, v);
+        azo_eci_to_ecef(r, sinG, cosG, tp);
+        for (size_t s = 0; s < n; s++) {
+            if (s == target_idx) continue;
+            double p[3];
+            azo_sgp4_propagate(&el[s], times[ti] + epoch_offsets[s], r, v);
+            azo_eci_to_ecef(r, sinG, cosG, p);
+            double dx = tp[0] - p[0], dy = tp[1] - p[1], dz = tp[2] - p[2];
+            double distSq = dx * dx + dy * dy + dz * dz;
+            if (distSq < outMinDists[s]) { outMinDists[s] = distSq; outMinT[s] = (uint32_t)ti; }
+        }
+    }
+    for (size_t i = 0; i < n; i++) outMinDists[i] = sqrt(outMinDists[i]); /* :753-755 */
+done:
+    free(el);
+    return rc;
+}

@@ -109,6 +109,12 @@ int azo_satrec_array_sgp4(const char *const *lines1, const char *const *lines2, 
                           const double *jd, const double *fr, size_t nt,
                           double *pos_satmajor, double *vel_satmajor);
 
+/* Constellation.screenConstellation (src/Constellation.zig:683-756): near-earth satellites only,
+ * tsince = times[t] + epoch_offsets[sat]; ECEF rotation by GMST(reference_jd + t/1440) as the reference. */
+int azo_screen_constellation(const char *const *lines1, const char *const *lines2, size_t n, int grav,
+                             const double *times, size_t nt, const double *epoch_offsets, size_t target_idx,
+                             double threshold, double reference_jd, double *out_min_dists, uint32_t *out_min_t);
+
 #ifdef __cplusplus
 }
 #endif

@@ -90,6 +90,10 @@ def lib() -> C.CDLL:
         L.azo_satrec_array_sgp4.argtypes = [
             C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int, dp, dp, C.c_size_t, dp, dp]
         L.azo_satrec_array_sgp4.restype = C.c_int
+        L.azo_screen_constellation.argtypes = [
+            C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int, dp, C.c_size_t, dp, C.c_size_t,
+            C.c_double, C.c_double, dp, C.POINTER(C.c_uint32)]
+        L.azo_screen_constellation.restype = C.c_int
         _lib = L
     return _lib
 
@@ -218,6 +222,22 @@ def satrec_array_sgp4(tles, jd, fr, grav: int = WGS72):
     if rc != 0:
         raise ValueError(f"oracle satrec_array init failed rc={rc}")
     return pos, vel
+
+
+def screen_constellation(tles, times, epoch_offsets, target: int, threshold: float, reference_jd: float = 0.0,
+                         grav: int = WGS72):
+    """Scalar oracle of Constellation.screenConstellation (src/Constellation.zig:683-756)."""
+    times = np.ascontiguousarray(times, dtype=np.float64)
+    off = np.ascontiguousarray(epoch_offsets, dtype=np.float64)
+    n = len(tles)
+    dist = np.zeros(n)
+    tidx = np.zeros(n, dtype=np.uint32)
+    a1, a2 = _lines(tles)
+    rc = lib().azo_screen_constellation(a1, a2, n, grav, _dp(times), len(times), _dp(off), target, float(threshold),
+                                        float(reference_jd), _dp(dist), tidx.ctypes.data_as(C.POINTER(C.c_uint32)))
+    if rc != 0:
+        raise ValueError(f"oracle screen failed rc={rc}")
+    return dist, tidx
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -344,3 +344,33 @@ def test_headline_grid_properties(az, oracle, synth):
     # end-to-end host API on pinned buffers gives the same block
     p_host, v_host = c.propagate(jd, fr, layout=0)
     assert np.array_equal(p_host[rows], ph) and np.array_equal(v_host[rows], vh)
+
+
+# ---------------------------------------------------------------------------------------------- next rows
+def test_fused_single_target_screen(az, oracle, synth):
+    """Constellation.screenConstellation (src/Constellation.zig:683-756) fused on the device: minimum distance
+    and its first time index per satellite against one target; 12 bytes per satellite come back."""
+    tles = synth.near_earth_catalog(700)
+    # make a few near-neighbours of the target so some minima fall below the threshold
+    base = tles[5]
+    for k in range(6):
+        l2 = base[1]
+        ma = (float(l2[43:51]) + 0.02 * (k + 1)) % 360.0
+        l2 = l2[:43] + f"{ma:8.4f}" + l2[51:68]
+        l2 = l2 + str(synth._checksum(l2))
+        tles[100 + k] = (base[0], l2)
+    c = az.Constellation(tles)
+    times = np.arange(0.0, 1440.0, 1.0)
+    ref = 2460437.5
+    off = (ref - c.epochs) * 1440.0
+    for target, thr in ((5, 50.0), (311, 500.0)):
+        d, ti = c.screen_conjunction(times, target, thr, epoch_offsets=off, reference_jd=ref)
+        do, tio = oracle.screen_constellation(tles, times, off, target, thr, ref)
+        assert d.shape == (700,) and ti.dtype == np.uint32
+        assert np.max(np.abs(d - do)) < 1e-6
+        assert d[target] == thr and ti[target] == 0
+        hit = do < thr
+        assert hit.sum() >= 3
+        same = ti == tio
+        # an index may differ only where two epochs tie to rounding
+        assert same[~hit].all() and (same[hit].mean() > 0.95)
