@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         "astroz_cuda_sgp4_epoch": (i32, [vp, dp]),
         "astroz_cuda_sgp4_propagate": (i32, [vp, C.c_double, dp, dp]),
         "astroz_cuda_sgp4_propagate_batch": (i32, [vp, dp, dp, u32]),
+        "astroz_cuda_sgp4_array": (i32, [vp, dp, dp, C.c_double, dp, u32]),
         "astroz_cuda_fp64_peak": (i32, [i32, dp]),
     }
     for name, (res, args) in sig.items():
@@ -103,7 +104,8 @@ EXPORTS = [
     "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sgp4_screen",
     "astroz_cuda_sgp4_init",
     "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch",
-    "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_fp64_peak",
+    "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",
+    "astroz_cuda_fp64_peak",
 ]
 
 
@@ -121,21 +123,67 @@ def as_f64(x) -> np.ndarray:
     return np.ascontiguousarray(np.atleast_1d(np.asarray(x, dtype=np.float64)))
 
 
+class _PinnedPool:
+    """Recycles cudaMallocHost blocks: page-locking is expensive (tens of ms per call, and cudaFreeHost
+    synchronises the device), while the python-sgp4 style API returns freshly allocated arrays on every
+    call.  Blocks whose arrays were garbage-collected are kept (up to ASTROZ_PINNED_POOL_MB, default 4096)
+    and handed out again for requests of a similar size."""
+
+    def __init__(self):
+        self.free: list[tuple[int, int]] = []   # (nbytes, ptr)
+        self.held = 0
+        self.cap = int(os.environ.get("ASTROZ_PINNED_POOL_MB", "4096")) << 20
+
+    def get(self, nbytes: int) -> tuple[int, int]:
+        best = None
+        for i, (sz, _) in enumerate(self.free):
+            if sz >= nbytes and sz <= nbytes + (nbytes >> 2) + 4096 and (best is None or sz < self.free[best][0]):
+                best = i
+        if best is not None:
+            sz, ptr = self.free.pop(best)
+            self.held -= sz
+            return sz, ptr
+        ptr = lib().astroz_cuda_host_alloc(nbytes)
+        if not ptr and self.free:       # make room and retry once
+            self.trim(0)
+            ptr = lib().astroz_cuda_host_alloc(nbytes)
+        if not ptr:
+            raise AstrozCudaError(-100, "cudaMallocHost failed")
+        return nbytes, ptr
+
+    def put(self, nbytes: int, ptr: int) -> None:
+        if nbytes > self.cap:
+            lib().astroz_cuda_host_free(ptr)
+            return
+        self.free.append((nbytes, ptr))
+        self.held += nbytes
+        self.trim(self.cap)
+
+    def trim(self, limit: int) -> None:
+        while self.free and self.held > limit:
+            sz, ptr = self.free.pop(0)
+            self.held -= sz
+            lib().astroz_cuda_host_free(ptr)
+
+
+_POOL = _PinnedPool()
+
+
 class _PinnedBlock:
-    """One cudaMallocHost block exposed through the array interface; freed when the last ndarray
-    viewing it is collected."""
+    """One cudaMallocHost block exposed through the array interface; returned to the pool when the last
+    ndarray viewing it is collected."""
 
     def __init__(self, nbytes: int):
         nbytes = max(int(nbytes), 8)
-        self._free = lib().astroz_cuda_host_free
-        self.ptr = lib().astroz_cuda_host_alloc(nbytes)
-        if not self.ptr:
-            raise AstrozCudaError(-100, "cudaMallocHost failed")
+        self.nbytes, self.ptr = _POOL.get(nbytes)
         self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 3}
 
     def __del__(self):
         if getattr(self, "ptr", None):
-            self._free(self.ptr)
+            try:
+                _POOL.put(self.nbytes, self.ptr)
+            except Exception:
+                pass
             self.ptr = None
 
 

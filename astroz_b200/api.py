@@ -117,12 +117,13 @@ class Satrec:
         """(e[n], r[n,3], v[n,3]); e is all zeros like the reference (api.py:171-180)."""
         jd, fr = as_f64(jd), as_f64(fr)
         n = jd.shape[0]
-        out = np.zeros((n, 6))
-        if self._h and n:
-            rc = lib().astroz_cuda_sgp4_propagate_batch(self._h, dptr(self._tsince(jd, fr)), dptr(out), n)
-            if rc not in _lib.SGP4_ERROR:
-                check(rc)
-        return np.zeros(n, dtype=np.uint8), np.ascontiguousarray(out[:, :3]), np.ascontiguousarray(out[:, 3:])
+        if not (self._h and n):
+            return np.zeros(n, dtype=np.uint8), np.zeros((n, 3)), np.zeros((n, 3))
+        out = _lib.pinned_empty((n, 6))  # x y z vx vy vz records, filled by one device->host copy
+        rc = lib().astroz_cuda_sgp4_array(self._h, dptr(jd), dptr(fr), self.jdsatepoch + self.jdsatepochF, dptr(out), n)
+        if rc not in _lib.SGP4_ERROR:
+            check(rc)
+        return np.zeros(n, dtype=np.uint8), out[:, :3], out[:, 3:]
 
 
 class SatrecArray:

@@ -570,7 +570,8 @@ int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float
 
 // ---- stateless near-earth path -----------------------------------------------------------------
 static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t nt, const double *epoch_offsets,
-                                double *dPos, double *dVel, int mode, double reference_jd, int layout, cudaStream_t s) {
+                                double *dPos, double *dVel, int mode, double reference_jd, int layout, cudaStream_t s,
+                                uint32_t recStride = 3) {
     const uint32_t ns = c->cat.nSgp4;
     const uint32_t padded = c->cat.sgp4Padded();
     int32_t rc = reserve_time(c, nt);
@@ -615,6 +616,7 @@ static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t 
     a.pos = dPos;
     a.vel = dVel;
     a.outNumSats = ns;
+    a.recStride = recStride;
     AZ_CUDA(cudaEventRecord(c->ev[0], s));
     AZ_CUDA(az::launch_sgp4_grid(a, mode, layout, s, c->variant));
     AZ_CUDA(cudaEventRecord(c->ev[1], s));
@@ -754,10 +756,22 @@ int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, d
     if (count == 0) return ASTROZ_OK;
     Constellation *c = s->c;
     AZ_CUDA(cudaSetDevice(c->device));
-    std::vector<double> pos((size_t)count * 3), vel((size_t)count * 3);
+    const bool fast = !s->deep && count >= 64;
+    std::vector<double> pos(fast ? 0 : (size_t)count * 3), vel(fast ? 0 : (size_t)count * 3);
     int32_t rc;
     if (!s->deep) {
+        // near earth: the time-parallel kernel writes x y z vx vy vz records straight into one block that
+        // is copied to `results` in a single transfer (src/c_api/sgp4.zig:60-100 layout)
         const double zero = 0.0;
+        if (count >= 64) {
+            AZ_CUDA(c->dPos.reserve((size_t)count * 6));
+            rc = sgp4_into_common(c, times, count, &zero, c->dPos.p, c->dPos.p + 3, ASTROZ_MODE_TEME, 0.0,
+                                  ASTROZ_LAYOUT_SATELLITE_MAJOR, c->stream, 6);
+            if (rc != ASTROZ_OK) return rc;
+            AZ_CUDA(cudaMemcpyAsync(results, c->dPos.p, (size_t)count * 48, cudaMemcpyDeviceToHost, c->stream));
+            AZ_CUDA(cudaStreamSynchronize(c->stream));
+            return ASTROZ_OK;
+        }
         rc = astroz_cuda_sgp4_propagate_into(c, times, count, &zero, pos.data(), vel.data(), ASTROZ_MODE_TEME, 0.0,
                                              ASTROZ_LAYOUT_SATELLITE_MAJOR);
         if (rc != ASTROZ_OK) return rc;
@@ -812,6 +826,53 @@ int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, d
         r[3] = vel[i * 3]; r[4] = vel[i * 3 + 1]; r[5] = vel[i * 3 + 2];
     }
     return rc;
+}
+
+int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *fr, double epoch_jd, double *results,
+                               uint32_t count) {
+    Sgp4Single *s = static_cast<Sgp4Single *>(h);
+    if (!s || !jd || !fr || !results) return ASTROZ_NULL_POINTER;
+    if (count == 0) return ASTROZ_OK;
+    Constellation *c = s->c;
+    if (s->deep || count < 64) {  // deep space / tiny: host-side tsince, then the batch entry point
+        std::vector<double> ts(count);
+        for (uint32_t i = 0; i < count; ++i) ts[i] = ((jd[i] + fr[i]) - epoch_jd) * 1440.0;
+        return astroz_cuda_sgp4_propagate_batch(h, ts.data(), results, count);
+    }
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = c->stream;
+    if (c->timePending) {
+        AZ_CUDA(cudaEventSynchronize(c->timeCopied));
+        c->timePending = false;
+    }
+    AZ_CUDA(c->dTime.reserve((size_t)count * 2));
+    AZ_CUDA(c->dPos.reserve((size_t)count * 6));
+    AZ_CUDA(cudaMemcpyAsync(c->dTime.p, jd, (size_t)count * 8, cudaMemcpyHostToDevice, st));
+    AZ_CUDA(cudaMemcpyAsync(c->dTime.p + count, fr, (size_t)count * 8, cudaMemcpyHostToDevice, st));
+    az::GridArgs a;
+    a.g = c->g;
+    a.sgp4Tiles = c->dTiles.p;
+    a.toff = c->dToff.p;
+    a.orig = c->dIdentity.p;
+    a.nSats = 1;
+    a.jdArr = c->dTime.p;
+    a.frArr = c->dTime.p + count;
+    a.tbase = c->dTime.p;
+    a.epochJd = epoch_jd;
+    a.nTimes = count;
+    a.pos = c->dPos.p;
+    a.vel = c->dPos.p + 3;
+    a.outNumSats = 1;
+    a.recStride = 6;
+    AZ_CUDA(cudaEventRecord(c->ev[0], st));
+    AZ_CUDA(az::launch_sgp4_grid(a, ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR, st, c->variant));
+    AZ_CUDA(cudaEventRecord(c->ev[1], st));
+    AZ_CUDA(cudaEventRecord(c->ev[2], st));
+    AZ_CUDA(cudaEventRecord(c->ev[3], st));
+    c->timed = true;
+    AZ_CUDA(cudaMemcpyAsync(results, c->dPos.p, (size_t)count * 48, cudaMemcpyDeviceToHost, st));
+    AZ_CUDA(cudaStreamSynchronize(st));
+    return ASTROZ_OK;
 }
 
 int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3], double vel[3]) {

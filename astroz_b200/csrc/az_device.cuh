@@ -454,26 +454,32 @@ AZ_HD void eci_to_ecef(double &x, double &y, double sinG, double cosG) {
     y = ey;
 }
 
+// Same fixed point as the reference's iteration lat <- atan2(z + e2 N sin(lat), p) (10 steps, exit at 1e-12,
+// src/WorldCoordinateSystem.zig:98-121), but iterated on (sin lat, cos lat) directly: no trigonometry
+// inside the loop (one rsqrt for N, one for the renormalisation), 6 steps (contraction ~e2 = 6.7e-3 per
+// step from the reference's own starting guess: < 1e-17 rad), then a single atan2 each for lat and lon.
 AZ_HD void ecef_to_geodetic(double &x, double &y, double &z) {
     constexpr double a = 6378.137;
     constexpr double f = 1.0 / 298.257223563;
     constexpr double e2 = 2.0 * f - f * f;
     const double lon = atan2(y, x);
-    const double p = sqrt(fma(x, x, y * y));
-    double lat = atan2(z, p * (1.0 - e2));
-#pragma unroll 1
-    for (int i = 0; i < 10; ++i) {
-        const double prev = lat;
-        const double sl = sin(lat);
-        const double N = a / sqrt(fma(-e2 * sl, sl, 1.0));
-        lat = atan2(fma(e2 * N, sl, z), p);
-        if (fabs(lat - prev) < 1e-12) break;
+    const double p2 = fma(x, x, y * y);
+    const double p = sqrt_from_rsqrt(p2, rsqrt_nr(p2));
+    double num = z, den = p * (1.0 - e2);
+    double h = rsqrt_nr(fma(num, num, den * den));
+    double sl = num * h, cl = den * h;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double N = a * rsqrt_nr(fma(-e2 * sl, sl, 1.0));
+        num = fma(e2 * N, sl, z);
+        h = rsqrt_nr(fma(num, num, p2));
+        sl = num * h;
+        cl = p * h;
     }
-    const double sl = sin(lat), cl = cos(lat);
-    const double N = a / sqrt(fma(-e2 * sl, sl, 1.0));
-    x = lat;
+    const double N = a * rsqrt_nr(fma(-e2 * sl, sl, 1.0));
+    x = atan2(sl, cl);
     y = lon;
-    z = p / cl - N;
+    z = p * rcp(cl) - N;
 }
 
 }  // namespace az

@@ -277,6 +277,59 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
     }
 }
 
+// K1t: one satellite x a long time axis (replaces sgp4Times8 / Sgp4.propagateN, src/simdKernels.zig:21-24,
+// src/Sgp4.zig:753-785; the path behind Satrec.sgp4_array and sgp4_propagate_batch).  With a single
+// satellite K1 would keep one warp per CTA busy; here every thread of every CTA takes epochs of that
+// satellite (kLanes each), its 33 constants sitting in shared memory.
+constexpr int kTimesThreads = 128;
+constexpr int kTimesLanes = 2;
+template <int kMode, bool kVel>
+__global__ void __launch_bounds__(kTimesThreads, 4) sgp4_times_kernel(const GridArgs a) {
+    __shared__ double cols[kSgp4Cols];
+    if (threadIdx.x < kSgp4Cols) cols[threadIdx.x] = __ldg(a.sgp4Tiles + threadIdx.x * kTileSats);  // lane 0 of tile 0
+    __syncthreads();
+    auto col = [&](int i) { return cols[i]; };
+    const double toff = __ldg(a.toff);
+    const uint32_t row = __ldg(a.orig);
+    const uint32_t base = blockIdx.x * (kTimesThreads * kTimesLanes) + threadIdx.x;
+    if (base >= a.nTimes) return;
+    double ts[kTimesLanes];
+#pragma unroll
+    for (int k = 0; k < kTimesLanes; ++k) {
+        const uint32_t tc = min(base + k * kTimesThreads, a.nTimes - 1);
+        ts[k] = a.jdArr ? ((__ldg(a.jdArr + tc) + __ldg(a.frArr + tc)) - a.epochJd) * 1440.0  // satrec.zig:263
+                        : __ldg(a.tbase + tc) + toff;
+    }
+    CellOut o[kTimesLanes];
+    sgp4_cell<kTimesLanes>(col, ts, a.g, o);
+#pragma unroll
+    for (int k = 0; k < kTimesLanes; ++k) {
+        const uint32_t t = base + k * kTimesThreads;
+        if (t < a.nTimes) {
+            if (a.status) a.status[(size_t)row * a.nTimes + t] = (o[k].mrt < 1.0) ? 1 : 0;
+            to_output_frame<kMode, kVel>(a, t, o[k]);
+            const size_t idx = ((size_t)row * a.nTimes + t) * a.recStride;
+            double *p = a.pos + idx;
+            __stcs(p, o[k].rx);
+            __stcs(p + 1, o[k].ry);
+            __stcs(p + 2, o[k].rz);
+            if (kVel) {
+                double *v = a.vel + idx;
+                __stcs(v, o[k].vx);
+                __stcs(v + 1, o[k].vy);
+                __stcs(v + 2, o[k].vz);
+            }
+        }
+    }
+}
+
+template <int kMode, bool kVel>
+static cudaError_t launch_k1t(const GridArgs &a, cudaStream_t stream) {
+    const uint32_t per = kTimesThreads * kTimesLanes;
+    sgp4_times_kernel<kMode, kVel><<<(a.nTimes + per - 1) / per, kTimesThreads, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
 struct Sgp4Variant {
     const char *name;
     int warps, stripe, minBlocks, lanes;
@@ -341,6 +394,14 @@ cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream
         return gv ? launch_k1<0, 0, true, AZ_DEFAULT_K1, 2>(a, stream) : launch_k1<0, 0, false, AZ_DEFAULT_K1, 2>(a, stream);
     }
     const bool vel = a.vel != nullptr;
+    if (a.nSats == 1 && a.nTimes >= 64) {  // single satellite: spread the time axis over the whole GPU
+        // one row: satellite-major and time-major coincide when the block has a single row
+        if (layout == 0 || a.outNumSats == 1) {
+            if (mode == 0) return vel ? launch_k1t<0, true>(a, stream) : launch_k1t<0, false>(a, stream);
+            if (mode == 1) return vel ? launch_k1t<1, true>(a, stream) : launch_k1t<1, false>(a, stream);
+            if (mode == 2) return vel ? launch_k1t<2, true>(a, stream) : launch_k1t<2, false>(a, stream);
+        }
+    }
 #define AZ_K1(L, M)                                                               \
     if (layout == L && mode == M)                                                 \
         return vel ? launch_k1_variant<L, M, true>(a, stream, variant)            \

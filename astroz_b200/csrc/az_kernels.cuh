@@ -22,6 +22,9 @@ struct GridArgs {
     const double *toff = nullptr;        // K1: per-satellite (reference - epoch) * 1440, padded
     const double *jdFull = nullptr;      // K2: jd + fr per epoch
     const double *tsince = nullptr;      // K2: if set, minutes since epoch are taken from here instead
+    const double *jdArr = nullptr;       // K1t: if set, tsince = ((jd[t] + fr[t]) - epochJd) * 1440 on the device
+    const double *frArr = nullptr;
+    double epochJd = 0.0;
     const double *gsin = nullptr;        // sin/cos(GMST) per epoch when mode != TEME
     const double *gcos = nullptr;
     uint32_t nTimes = 0;
@@ -30,6 +33,7 @@ struct GridArgs {
     double *vel = nullptr;               // nullable
     uint8_t *status = nullptr;           // nullable, [outRow][nTimes]
     uint32_t outNumSats = 0;             // row count of the output block (time-major stride)
+    uint32_t recStride = 3;              // K1t only: doubles between consecutive epochs (6 = x y z vx vy vz records)
     // fused all-gather (satellite-major only): when gather != 0 the result block is written to every GPU
     // of the box from inside the kernel -- gather 1: one multimem.st per 16 bytes to the NVLS multicast
     // mapping of the symmetric buffer (mcPos/mcVel); gather 2: plain stores to each peer mapping.

@@ -176,6 +176,12 @@ int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3]
 /* count times (minutes since epoch); results[count][6] = x y z vx vy vz (src/c_api/sgp4.zig:60-100) */
 int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, double *results, uint32_t count);
 
+/* Satrec.sgp4_array_into(jd, fr, positions, velocities) (bindings/python/src/satrec.zig:299-343): count absolute
+ * epochs jd[i] + fr[i]; tsince = ((jd + fr) - epoch_jd) * 1440 is formed on the device in fp64 (the same
+ * expression, :263).  results[count][6] = x y z vx vy vz.  Near-earth objects run on the time-parallel kernel. */
+int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *fr, double epoch_jd, double *results,
+                               uint32_t count);
+
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* DFMA microbenchmark on `device`: achieved fp64 TFLOP/s (FMA = 2) -- the measured roofline denominator */
 int32_t astroz_cuda_fp64_peak(int32_t device, double *tflops);

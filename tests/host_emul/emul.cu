@@ -75,3 +75,11 @@ extern "C" int emul_constellation_propagate(const char *const *l1, const char *c
 extern "C" void emul_sincos(const double *x, int n, double *s, double *c) {
     for (int i = 0; i < n; ++i) sincos_full(x[i], s[i], c[i]);
 }
+
+extern "C" void emul_ecef_to_geodetic(const double *ecef, int n, double *lla) {
+    for (int i = 0; i < n; ++i) {
+        double x = ecef[3 * i], y = ecef[3 * i + 1], z = ecef[3 * i + 2];
+        ecef_to_geodetic(x, y, z);
+        lla[3 * i] = x; lla[3 * i + 1] = y; lla[3 * i + 2] = z;
+    }
+}

@@ -374,3 +374,26 @@ def test_fused_single_target_screen(az, oracle, synth):
         same = ti == tio
         # an index may differ only where two epochs tie to rounding
         assert same[~hit].all() and (same[hit].mean() > 0.95)
+
+
+def test_single_satellite_long_time_axis(az, oracle):
+    """Satrec.sgp4_array over a long axis (the reference's other published benchmark family,
+    benchmarks/zig_sgp4_bench.zig:46-52): 1 satellite x 200k epochs runs on the dedicated time-parallel kernel
+    and must agree with the grid kernel and the oracle."""
+    from astroz_b200.api import Satrec, WGS72
+
+    sat = Satrec.twoline2rv(*G.ISS, WGS72)
+    n = 200_003
+    jd = np.full(n, sat.jdsatepoch)
+    fr = sat.jdsatepochF + np.arange(n) * (1.0 / 86400.0)
+    e, r, v = sat.sgp4_array(jd, fr)
+    ts = ((jd + fr) - (sat.jdsatepoch + sat.jdsatepochF)) * 1440.0
+    ref = oracle.Sgp4(*G.ISS, grav=oracle.WGS72)
+    idx = np.r_[0:40, n - 40:n, np.arange(0, n, 4999)]
+    ro = np.array([ref.propagate(ts[i]) for i in idx])
+    assert _maxerr(r[idx], ro[:, 0]) < POS_TOL and _maxerr(v[idx], ro[:, 1]) < VEL_TOL
+    assert np.isfinite(r).all() and np.isfinite(v).all()
+    # same satellite through the grid kernel (2 copies -> K1) gives the same numbers
+    c = az.Constellation([G.ISS, G.ISS])
+    p2, v2 = c.propagate(jd[:3000], fr[:3000], layout=0)
+    assert _maxerr(p2[0], r[:3000]) < 1e-6 and np.array_equal(p2[0], p2[1])

@@ -84,3 +84,18 @@ def test_cores_error_cells(emul, oracle):
     assert np.all(pe[1][err[1] != 0] == 0.0)
     ok = err == 0
     assert np.max(np.abs(po[ok] - pe[ok])) < 1e-5
+
+
+def test_geodetic_epilogue_matches_reference_iteration(emul, oracle):
+    # src/WorldCoordinateSystem.zig:98-121 (radians, km)
+    rng = np.random.default_rng(3)
+    r = 6378.137 + rng.uniform(150.0, 42000.0, 4000)
+    lat = rng.uniform(-1.55, 1.55, 4000)
+    lon = rng.uniform(-np.pi, np.pi, 4000)
+    ecef = np.stack([r * np.cos(lat) * np.cos(lon), r * np.cos(lat) * np.sin(lon), r * np.sin(lat)], axis=1).copy()
+    out = np.zeros_like(ecef)
+    dp = C.POINTER(C.c_double)
+    emul.lib.emul_ecef_to_geodetic(ecef.ctypes.data_as(dp), len(ecef), out.ctypes.data_as(dp))
+    ref = np.array([oracle.ecef_to_geodetic(e) for e in ecef])
+    assert np.max(np.abs(out[:, :2] - ref[:, :2])) < 1e-12
+    assert np.max(np.abs(out[:, 2] - ref[:, 2])) < 1e-7
