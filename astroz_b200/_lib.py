@@ -69,6 +69,7 @@ def lib() -> C.CDLL:
         "astroz_cuda_constellation_propagate_device": (i32, [vp, dp, dp, u32, vp, vp, vp, i32, i32, u32, u32, vp]),
         "astroz_cuda_constellation_propagate_gather": (i32, [vp, dp, dp, u32, C.POINTER(vp), C.POINTER(vp), u32, vp, vp,
                                                              u32, u32, vp]),
+        "astroz_cuda_constellation_propagate_device_f32": (i32, [vp, dp, dp, u32, vp, vp, i32, vp]),
         "astroz_cuda_constellation_reset_carry": (i32, [vp]),
         "astroz_cuda_constellation_synchronize": (i32, [vp]),
         "astroz_cuda_constellation_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
@@ -99,7 +100,7 @@ EXPORTS = [
     "astroz_cuda_constellation_classes", "astroz_cuda_constellation_get_reference_epoch",
     "astroz_cuda_constellation_set_reference_epoch", "astroz_cuda_constellation_propagate",
     "astroz_cuda_constellation_propagate_device", "astroz_cuda_constellation_propagate_gather",
-    "astroz_cuda_constellation_reset_carry",
+    "astroz_cuda_constellation_propagate_device_f32", "astroz_cuda_constellation_reset_carry",
     "astroz_cuda_constellation_synchronize", "astroz_cuda_constellation_last_kernel_ms",
     "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sgp4_screen",
     "astroz_cuda_sgp4_init",

@@ -169,6 +169,14 @@ class Constellation:
             C.c_void_p(mc_pos) if mc_pos else None, C.c_void_p(mc_vel) if mc_vel else None,
             rows, int(out_sat_offset), C.c_void_p(stream) if stream else None))
 
+    def propagate_device_f32(self, jd, fr, pos, vel, phase64: bool = True, stream: int = 0) -> None:
+        """BASELINE config 5 precision study: the near-earth satellites in fp32 arithmetic (phase64: secular
+        angles in fp64 first).  pos / vel: (n_sats, n_times, 3) float64 CUDA tensors."""
+        jd, fr = as_f64(jd), as_f64(fr)
+        check(lib().astroz_cuda_constellation_propagate_device_f32(
+            self._h, dptr(jd), dptr(fr), jd.shape[0], C.c_void_p(pos.data_ptr()), C.c_void_p(vel.data_ptr()),
+            1 if phase64 else 0, C.c_void_p(stream) if stream else None))
+
     def synchronize(self) -> None:
         check(lib().astroz_cuda_constellation_synchronize(self._h))
 

@@ -443,6 +443,37 @@ int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, con
     return rc;
 }
 
+int32_t astroz_cuda_constellation_propagate_device_f32(astroz_constellation_t h, const double *jd, const double *fr,
+                                                       uint32_t n_times, double *d_pos, double *d_vel, int32_t phase64,
+                                                       void *stream) {
+    Constellation *c = static_cast<Constellation *>(h);
+    if (!c || !jd || !fr || !d_pos || !d_vel) return ASTROZ_NULL_POINTER;
+    if (n_times == 0 || c->cat.nSgp4 == 0) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    double jdMin, jdMax;
+    int32_t rc = upload_time_axis(c, jd, fr, n_times, ASTROZ_MODE_TEME, s, &jdMin, &jdMax);
+    if (rc != ASTROZ_OK) return rc;
+    az::GridArgs a;
+    a.g = c->g;
+    a.sgp4Tiles = c->dTiles.p;
+    a.toff = c->dToff.p;
+    a.orig = c->dSgp4Orig.p;
+    a.nSats = c->cat.nSgp4;
+    a.tbase = c->dTime.p;
+    a.nTimes = n_times;
+    a.pos = d_pos;
+    a.vel = d_vel;
+    a.outNumSats = c->cat.n;
+    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    AZ_CUDA(az::launch_sgp4_grid_f32(a, phase64, s));
+    AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = true;
+    return ASTROZ_OK;
+}
+
 int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, const double *jd, const double *fr,
                                                    uint32_t n_times, void *const *peer_pos, void *const *peer_vel,
                                                    uint32_t n_peers, void *mc_pos, void *mc_vel, uint32_t out_num_sats,

@@ -14,6 +14,7 @@
 // (same eccentricity).  All arithmetic is fp64 on the CUDA cores; there is no contraction to give the
 // tensor cores.
 #include "az_kernels.cuh"
+#include "az_device_f32.cuh"
 
 #include <algorithm>
 
@@ -616,6 +617,50 @@ cudaError_t launch_sgp4_screen(const ScreenArgs &a, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     const uint32_t tiles = (a.nSats + kTileSats - 1) / kTileSats;
     sgp4_screen_kernel<<<tiles, kScreenWarps * 32, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp32 precision-study kernel (BASELINE config 5; no reference path).  Same mapping as K1.
+// ---------------------------------------------------------------------------------------------------
+template <bool kPhase64>
+__global__ void __launch_bounds__(128, 4) sgp4_grid_f32_kernel(const GridArgs a) {
+    __shared__ __align__(128) double tile[kSgp4TileDoubles];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tileIdx = blockIdx.x;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, kSgp4TileBytes);
+        tma_bulk_g2s(tile, a.sgp4Tiles + (size_t)tileIdx * kSgp4TileDoubles, kSgp4TileBytes, &bar);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t0 = blockIdx.y * 256, t1 = min(t0 + 256u, a.nTimes);
+    mbar_wait(&bar, 0);
+#pragma unroll 1
+    for (int sl = warp; sl < kTileSats; sl += 4) {
+        const uint32_t sat = tileIdx * kTileSats + sl;
+        if (sat >= a.nSats) break;
+        const double *colBase = tile + sl;
+        auto col = [colBase](int i) { return colBase[i * kTileSats]; };
+        const double toff = __ldg(a.toff + sat);
+        const uint32_t row = __ldg(a.orig + sat);
+#pragma unroll 1
+        for (uint32_t t = t0 + lane; t < t1; t += 32) {
+            CellOut o;
+            sgp4_cell_f32<kPhase64>(col, __ldg(a.tbase + t) + toff, a.g, o);
+            store_direct<0, true>(a, row, t, o);
+        }
+    }
+}
+
+cudaError_t launch_sgp4_grid_f32(const GridArgs &a, int phase64, cudaStream_t stream) {
+    const uint32_t tiles = (a.nSats + kTileSats - 1) / kTileSats, stripes = (a.nTimes + 255) / 256;
+    if (tiles == 0 || stripes == 0) return cudaSuccess;
+    if (!a.vel) return cudaErrorInvalidValue;
+    dim3 grid(tiles, stripes);
+    if (phase64) sgp4_grid_f32_kernel<true><<<grid, 128, 0, stream>>>(a);
+    else sgp4_grid_f32_kernel<false><<<grid, 128, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

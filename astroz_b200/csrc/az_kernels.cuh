@@ -70,6 +70,10 @@ struct ScreenArgs {
 };
 cudaError_t launch_sgp4_screen(const ScreenArgs &a, cudaStream_t stream);
 
+// fp32 study kernel (BASELINE config 5): same grid / layout as K1 (satellite-major TEME, fp64 output words),
+// arithmetic in fp32; phase64 != 0 forms the secular angles in fp64 first.
+cudaError_t launch_sgp4_grid_f32(const GridArgs &a, int phase64, cudaStream_t stream);
+
 // DFMA throughput microbenchmark: returns achieved fp64 FLOP/s (FMA = 2).
 cudaError_t measure_fp64_peak(double *flops);
 

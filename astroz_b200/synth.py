@@ -144,3 +144,25 @@ def mixed_catalog(n: int = HEADLINE_SATS, seed: int = 28626, n_geo: int = 1024, 
 def time_grid(n_times: int = HEADLINE_TIMES, jd0: float = BENCH_JD0) -> tuple[np.ndarray, np.ndarray]:
     """1-minute steps: jd = jd0, fr = i/1440 (README.md:35)."""
     return np.full(n_times, jd0, dtype=np.float64), np.arange(n_times, dtype=np.float64) / 1440.0
+
+
+def monte_carlo_catalog(n: int = 10000, seed: int = 12345, base: tuple[str, str] | None = None) -> list[tuple[str, str]]:
+    """BASELINE config 5: n perturbed element sets of one object (ISS TLE of src/Sgp4.zig:909-910 by default).
+    Additive Gaussian draws, seed 12345 (the seed of the reference's Monte-Carlo test, src/MonteCarlo.zig:293):
+    sigma_i = sigma_RAAN = sigma_argp = sigma_M = 0.01 deg, sigma_e = 1e-5 (floored at 1e-7), sigma_n = 1e-5 rev/day,
+    sigma_B* = 10 %.  There is no reference code path for perturbed-TLE draws (MonteCarlo.zig samples Hohmann
+    transfers); the workload is defined here."""
+    l1, l2 = base or ("1 25544U 98067A   24127.82853009  .00015698  00000+0  27310-3 0  9995",
+                      "2 25544  51.6393 160.4574 0003580 140.6673 205.7250 15.50957674452123")
+    incl, raan, ecc = float(l2[8:16]), float(l2[17:25]), float(l2[26:33]) / 1e7
+    argp, ma, nn = float(l2[34:42]), float(l2[43:51]), float(l2[52:63])
+    bstar = float(l1[53:59]) * 1e-5 * 10.0 ** int(l1[59:61])
+    yy, doy = int(l1[18:20]), float(l1[20:32])
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        out.append(tle_lines(
+            20000 + i, yy, doy, incl + rng.normal(0, 0.01), raan + rng.normal(0, 0.01),
+            max(ecc + rng.normal(0, 1e-5), 1e-7), argp + rng.normal(0, 0.01), ma + rng.normal(0, 0.01),
+            nn + rng.normal(0, 1e-5), bstar * (1.0 + rng.normal(0, 0.1))))
+    return out

@@ -182,6 +182,14 @@ int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, d
 int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *fr, double epoch_jd, double *results,
                                uint32_t count);
 
+/* BASELINE config 5 (fp32 tolerance study; defined by this project, the reference has no such path): the
+ * near-earth satellites of `h` propagated with the arithmetic in fp32 -- phase64 = 0: everything in fp32;
+ * phase64 = 1: the three secular angles formed and reduced in fp64, the rest in fp32.  Satellite-major TEME,
+ * results widened to fp64 words so they can be compared with astroz_cuda_constellation_propagate_device. */
+int32_t astroz_cuda_constellation_propagate_device_f32(astroz_constellation_t h, const double *jd, const double *fr,
+                                                       uint32_t n_times, double *d_pos, double *d_vel, int32_t phase64,
+                                                       void *stream);
+
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* DFMA microbenchmark on `device`: achieved fp64 TFLOP/s (FMA = 2) -- the measured roofline denominator */
 int32_t astroz_cuda_fp64_peak(int32_t device, double *tflops);

@@ -397,3 +397,28 @@ def test_single_satellite_long_time_axis(az, oracle):
     c = az.Constellation([G.ISS, G.ISS])
     p2, v2 = c.propagate(jd[:3000], fr[:3000], layout=0)
     assert _maxerr(p2[0], r[:3000]) < 1e-6 and np.array_equal(p2[0], p2[1])
+
+
+def test_config5_monte_carlo_draws_and_fp32_study(az, oracle, synth):
+    """BASELINE config 5: perturbed draws of one object.  fp64 kernel vs oracle at the usual tolerance; the fp32
+    study kernels must stay within the (much looser) envelope single precision allows."""
+    import torch
+
+    tles = synth.monte_carlo_catalog(400)
+    jd, fr = synth.time_grid(1440, jd0=2460437.5)
+    jd, fr = jd[::16].copy(), fr[::16].copy()
+    c = az.Constellation(tles)
+    assert c.numSgp4 == 400
+    p, v = c.propagate(jd, fr, layout=0)
+    po, vo, err, _ = oracle.constellation_propagate(tles, jd, fr)
+    assert _maxerr(p, po) < POS_TOL and _maxerr(v, vo) < VEL_TOL
+    spread = np.linalg.norm(p - p.mean(axis=0), axis=2).max()
+    assert 1.0 < spread < 500.0          # the draws really differ (0.01 deg ~ 1 km) but stay one object
+    dev = torch.device("cuda", 0)
+    p64 = torch.as_tensor(p, device=dev)
+    for phase, tol in ((True, 0.05), (False, 5.0)):
+        p32 = torch.empty_like(p64)
+        v32 = torch.empty_like(p64)
+        c.propagate_device_f32(jd, fr, p32, v32, phase64=phase)
+        c.synchronize()
+        assert float((p32 - p64).abs().max()) < tol
