@@ -72,15 +72,24 @@ struct Constellation {
     DevBuf<uint32_t> dSgp4Orig, dSdp4Orig, dIdentity;
     DevBuf<az::Sdp4Sat> dSdp4;
     // per-call time axis: tbase | jdFull | gsin | gcos
+    // host staging rotates over kSlots pinned buffers so the host can queue several calls ahead of the GPU
+    // without stalling on the previous call's asynchronous upload
+    static constexpr int kSlots = 4;
     DevBuf<double> dTime;
-    double *hTime = nullptr;
-    size_t hTimeCap = 0;
-    cudaEvent_t timeCopied = nullptr;
-    bool timePending = false;
+    double *hTimeSlot[kSlots] = {};
+    size_t hTimeSlotCap[kSlots] = {};
+    cudaEvent_t slotCopied[kSlots] = {};
+    bool slotPending[kSlots] = {};
+    int slot = 0;
+    double *hTime = nullptr;          // the slot in use by the current call
+    cudaEvent_t timeCopied = nullptr;  // its event
+    bool timePending = false;          // kept for call sites: set after recording timeCopied
     // stateless-path epoch offsets
     DevBuf<double> dToffCall;
     double *hToffCall = nullptr;
     size_t hToffCap = 0;
+    cudaEvent_t toffCopied = nullptr;
+    bool toffPending = false;
     // resonance lattice (depends on the elements only; grown when a call reaches further in time)
     DevBuf<double2> dLattice;
     int latticeNodes = 0;
@@ -97,9 +106,10 @@ struct Constellation {
         cudaSetDevice(device);
         dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release();
         dSdp4.release(); dTime.release(); dToffCall.release(); dLattice.release(); dPos.release(); dVel.release();
-        if (hTime) cudaFreeHost(hTime);
+        for (auto &h : hTimeSlot) if (h) cudaFreeHost(h);
         if (hToffCall) cudaFreeHost(hToffCall);
-        if (timeCopied) cudaEventDestroy(timeCopied);
+        for (auto &e : slotCopied) if (e) cudaEventDestroy(e);
+        if (toffCopied) cudaEventDestroy(toffCopied);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : chunkDone) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -132,7 +142,9 @@ int32_t finish_create(Constellation *c, int device) {
     AZ_CUDA(cudaSetDevice(device));
     AZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     AZ_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
-    AZ_CUDA(cudaEventCreateWithFlags(&c->timeCopied, cudaEventDisableTiming));
+    for (auto &e : c->slotCopied) AZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    AZ_CUDA(cudaEventCreateWithFlags(&c->toffCopied, cudaEventDisableTiming));
+    c->timeCopied = c->slotCopied[0];
     for (auto &ev : c->ev) AZ_CUDA(cudaEventCreate(&ev));
     for (auto &ev : c->chunkDone) AZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     c->g = az::grav_consts(c->cat.grav);
@@ -162,17 +174,24 @@ int32_t finish_create(Constellation *c, int device) {
 
 // host staging for the time axis; waits for the previous call's async upload before reuse
 int32_t reserve_time(Constellation *c, size_t nt) {
-    if (c->timePending) {
-        AZ_CUDA(cudaEventSynchronize(c->timeCopied));
-        c->timePending = false;
+    // the call that last used the current slot recorded slotCopied[slot] (timePending tells us so)
+    if (c->timePending) c->slotPending[c->slot] = true;
+    c->timePending = false;
+    c->slot = (c->slot + 1) % Constellation::kSlots;
+    const int k = c->slot;
+    if (c->slotPending[k]) {  // kSlots calls ago: almost always long finished
+        AZ_CUDA(cudaEventSynchronize(c->slotCopied[k]));
+        c->slotPending[k] = false;
     }
-    if (nt * 4 > c->hTimeCap) {
-        if (c->hTime) cudaFreeHost(c->hTime);
-        c->hTime = nullptr;
-        c->hTimeCap = 0;
-        AZ_CUDA(cudaMallocHost(&c->hTime, nt * 4 * 8));
-        c->hTimeCap = nt * 4;
+    if (nt * 4 > c->hTimeSlotCap[k]) {
+        if (c->hTimeSlot[k]) cudaFreeHost(c->hTimeSlot[k]);
+        c->hTimeSlot[k] = nullptr;
+        c->hTimeSlotCap[k] = 0;
+        AZ_CUDA(cudaMallocHost(&c->hTimeSlot[k], nt * 4 * 8));
+        c->hTimeSlotCap[k] = nt * 4;
     }
+    c->hTime = c->hTimeSlot[k];
+    c->timeCopied = c->slotCopied[k];
     AZ_CUDA(c->dTime.reserve(nt * 4));
     return ASTROZ_OK;
 }
@@ -622,6 +641,10 @@ static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t 
         AZ_CUDA(cudaMemcpyAsync(c->dTime.p + 2 * cap, gs, (size_t)nt * 8, cudaMemcpyHostToDevice, s));
         AZ_CUDA(cudaMemcpyAsync(c->dTime.p + 3 * cap, gc, (size_t)nt * 8, cudaMemcpyHostToDevice, s));
     }
+    if (c->toffPending) {  // the previous call's upload of the offsets must have left the staging buffer
+        AZ_CUDA(cudaEventSynchronize(c->toffCopied));
+        c->toffPending = false;
+    }
     if (padded > c->hToffCap) {
         if (c->hToffCall) cudaFreeHost(c->hToffCall);
         c->hToffCall = nullptr;
@@ -631,6 +654,8 @@ static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t 
     for (uint32_t i = 0; i < padded; ++i) c->hToffCall[i] = epoch_offsets[std::min(i, ns - 1)];
     AZ_CUDA(c->dToffCall.reserve(padded));
     AZ_CUDA(cudaMemcpyAsync(c->dToffCall.p, c->hToffCall, (size_t)padded * 8, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaEventRecord(c->toffCopied, s));
+    c->toffPending = true;
     AZ_CUDA(cudaEventRecord(c->timeCopied, s));
     c->timePending = true;
 
@@ -709,6 +734,10 @@ int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, u
     if (rc != ASTROZ_OK) return rc;
     for (uint32_t t = 0; t < n_times; ++t) c->hTime[t] = times[t];
     AZ_CUDA(cudaMemcpyAsync(c->dTime.p, c->hTime, (size_t)n_times * 8, cudaMemcpyHostToDevice, s));
+    if (c->toffPending) {  // the previous call's upload of the offsets must have left the staging buffer
+        AZ_CUDA(cudaEventSynchronize(c->toffCopied));
+        c->toffPending = false;
+    }
     if (padded > c->hToffCap) {
         if (c->hToffCall) cudaFreeHost(c->hToffCall);
         c->hToffCall = nullptr;
@@ -718,6 +747,8 @@ int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, u
     for (uint32_t i = 0; i < padded; ++i) c->hToffCall[i] = epoch_offsets[std::min(i, ns - 1)];
     AZ_CUDA(c->dToffCall.reserve(padded));
     AZ_CUDA(cudaMemcpyAsync(c->dToffCall.p, c->hToffCall, (size_t)padded * 8, cudaMemcpyHostToDevice, s));
+    AZ_CUDA(cudaEventRecord(c->toffCopied, s));
+    c->toffPending = true;
     AZ_CUDA(cudaEventRecord(c->timeCopied, s));
     c->timePending = true;
     // scratch: target track [nt][3] | minDist [ns] | minT [ns] (as doubles' worth of space)
@@ -872,10 +903,6 @@ int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *
     }
     AZ_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
-    if (c->timePending) {
-        AZ_CUDA(cudaEventSynchronize(c->timeCopied));
-        c->timePending = false;
-    }
     AZ_CUDA(c->dTime.reserve((size_t)count * 2));
     AZ_CUDA(c->dPos.reserve((size_t)count * 6));
     AZ_CUDA(cudaMemcpyAsync(c->dTime.p, jd, (size_t)count * 8, cudaMemcpyHostToDevice, st));
