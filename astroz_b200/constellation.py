@@ -72,6 +72,26 @@ class Constellation:
         self.device, self.grav = int(device), int(grav)
         return self
 
+    @classmethod
+    def from_elements(cls, epoch_jd, mean_motion_rev_day, ecc, incl_deg, raan_deg, argp_deg, ma_deg, bstar,
+                      grav: int = _lib.WGS72, device: int = 0) -> "Constellation":
+        """Build from numeric mean elements (what Tle.parseOmm extracts from an OMM record, src/Tle.zig:134-215):
+        no TLE text round trip, so e.g. Monte-Carlo draws keep their full fp64 values."""
+        cols = [as_f64(a) for a in (epoch_jd, mean_motion_rev_day, ecc, incl_deg, raan_deg, argp_deg, ma_deg, bstar)]
+        n = cols[0].shape[0]
+        if any(c.shape[0] != n for c in cols):
+            raise ValueError("element arrays must have the same length")
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._free = lib().astroz_cuda_constellation_free
+        check(lib().astroz_cuda_constellation_create_from_elements(*[dptr(c) for c in cols], n, int(grav), int(device),
+                                                                    C.byref(self._h)))
+        cn, ns, nd = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().astroz_cuda_constellation_counts(self._h, C.byref(cn), C.byref(ns), C.byref(nd)))
+        self.numSatellites, self.numSgp4, self.numSdp4 = cn.value, ns.value, nd.value
+        self.device, self.grav = int(device), int(grav)
+        return self
+
     def deinit(self) -> None:
         """Constellation.deinit (src/Constellation.zig:202-210)."""
         if getattr(self, "_h", None) is not None and self._h:

@@ -395,6 +395,43 @@ int32_t astroz_cuda_constellation_create_from_text(const char *text, size_t len,
     return astroz_cuda_constellation_create(p1.data(), p2.data(), (uint32_t)l1.size(), grav, device, out);
 }
 
+int32_t astroz_cuda_constellation_create_from_elements(const double *epoch_jd, const double *mean_motion_rev_day,
+                                                       const double *ecc, const double *incl_deg, const double *raan_deg,
+                                                       const double *argp_deg, const double *ma_deg, const double *bstar,
+                                                       uint32_t n, int32_t grav, int32_t device,
+                                                       astroz_constellation_t *out) {
+    if (!out || (n && (!epoch_jd || !mean_motion_rev_day || !ecc || !incl_deg || !raan_deg || !argp_deg || !ma_deg || !bstar)))
+        return ASTROZ_NULL_POINTER;
+    *out = nullptr;
+    std::vector<az::TleRecord> recs(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        az::TleRecord &t = recs[i];
+        t.satnum = i;
+        t.epochJd = epoch_jd[i];
+        t.revPerDay = mean_motion_rev_day[i];
+        t.ecc = ecc[i];
+        t.inclDeg = incl_deg[i];
+        t.raanDeg = raan_deg[i];
+        t.argpDeg = argp_deg[i];
+        t.maDeg = ma_deg[i];
+        t.bstar = bstar[i];
+    }
+    Constellation *c = new (std::nothrow) Constellation();
+    if (!c) return ASTROZ_ALLOC_FAILED;
+    int rc = az::build_catalog_records(recs.data(), n, grav, c->cat);
+    if (rc != az::kOk) {
+        delete c;
+        return status_to_code(rc);
+    }
+    int32_t e = finish_create(c, device);
+    if (e != ASTROZ_OK) {
+        delete c;
+        return e;
+    }
+    *out = c;
+    return ASTROZ_OK;
+}
+
 void astroz_cuda_constellation_free(astroz_constellation_t h) { delete static_cast<Constellation *>(h); }
 
 int32_t astroz_cuda_constellation_counts(astroz_constellation_t h, uint32_t *n, uint32_t *ns, uint32_t *nd) {

@@ -70,8 +70,9 @@ struct CatalogTables {
     uint32_t sgp4Padded() const { return sgp4Tiles_count() * kTileSats; }
 };
 
-// Classify and tabulate.  Returns kOk or the first non-deep-space init failure (src/Constellation.zig:115-126).
-inline int build_catalog(const char *const *l1, const char *const *l2, uint32_t n, int gravSel, CatalogTables &out) {
+// Classify and tabulate parsed element sets.  Returns kOk or the first non-deep-space init failure
+// (src/Constellation.zig:115-126).
+inline int build_catalog_records(const TleRecord *recs, uint32_t n, int gravSel, CatalogTables &out) {
     out = CatalogTables{};
     out.n = n;
     out.grav = gravity(gravSel);
@@ -80,8 +81,7 @@ inline int build_catalog(const char *const *l1, const char *const *l2, uint32_t 
     std::vector<NearEarth> near;
     near.reserve(n);
     for (uint32_t i = 0; i < n; ++i) {
-        TleRecord t;
-        if (parse_tle(l1[i], l2[i], t) != kOk) return kBadTle;
+        const TleRecord &t = recs[i];
         out.epochs[i] = t.epochJd;
         NearEarth ne;
         int rc = build_near_earth(t, out.grav, ne);
@@ -118,6 +118,14 @@ inline int build_catalog(const char *const *l1, const char *const *l2, uint32_t 
         if (s >= out.nSgp4) out.sgp4Orig[s] = out.sgp4Orig[out.nSgp4 - 1];
     }
     return kOk;
+}
+
+// From TLE text lines (src/Tle.zig:49-101).
+inline int build_catalog(const char *const *l1, const char *const *l2, uint32_t n, int gravSel, CatalogTables &out) {
+    std::vector<TleRecord> recs(n);
+    for (uint32_t i = 0; i < n; ++i)
+        if (parse_tle(l1[i], l2[i], recs[i]) != kOk) return kBadTle;
+    return build_catalog_records(recs.data(), n, gravSel, out);
 }
 
 // Split a text blob into element-set line pairs (src/Tle.zig:103-132 MultiIterator semantics).

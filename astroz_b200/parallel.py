@@ -137,3 +137,37 @@ def propagate_gather(sp: ShardedPropagator, sym: SymmetricBlock, jd, fr, velocit
     else:
         sp.local.propagate_gather(jd, fr, peer_pos=sym.peer_pos, peer_vel=sym.peer_vel if velocities else None,
                                   out_num_sats=sp.padded_rows, out_sat_offset=sp.rank * sp.rows, stream=stream)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, so pinned host buffers are allocated
+    (first touch) next to the GPU's PCIe root.  Each GPU has its own Gen5 x16 link; with one process per GPU
+    and node-local staging the per-GPU device->host rate holds as N grows.  Best effort: returns what it did."""
+    import glob
+    import os
+
+    info = {"device": device_index, "numa_node": None, "cpus": None}
+    try:
+        import torch
+
+        props = torch.cuda.get_device_properties(device_index)
+        bus = f"{getattr(props, 'pci_domain_id', 0):04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        path = f"/sys/bus/pci/devices/{bus}/numa_node"
+        if not os.path.exists(path):
+            cands = glob.glob(f"/sys/bus/pci/devices/*:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0/numa_node")
+            path = cands[0] if cands else path
+        node = int(open(path).read().strip())
+        if node < 0:
+            return info
+        cpulist = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(numa_node=node, cpus=len(allowed))
+    except Exception as exc:  # sysfs layout differs / no permission: keep the default affinity
+        info["error"] = repr(exc)[:120]
+    return info

@@ -194,6 +194,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from astroz_b200.parallel import bind_to_gpu_numa_node
+
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # host staging next to this GPU's PCIe root
 
     tles, jd, fr, desc = workload(args.workload, rank)
     c = Constellation(tles, device=local_rank)
@@ -397,7 +400,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                    "parallelism": f"satellite-sharded x{world}, no data-path collective in `value`"},
         "e2e": {"value": e2e_value, "unit": "props/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "d2h_GBs": d2h / e2e_s / 1e9,
-                "api": "Constellation.propagate(jd, fr, pos, vel) with pinned host buffers", "checksum": checksum},
+                "api": "Constellation.propagate(jd, fr, pos, vel) with pinned host buffers", "checksum": checksum,
+                "numa_binding_rank0": numa},
         "e2e_screen": screen,
         "gpu_launches": kernels_per_step * args.steps,
         "clocks": clocks,

@@ -80,6 +80,15 @@ int32_t astroz_cuda_constellation_create(const char *const *line1, const char *c
 int32_t astroz_cuda_constellation_create_from_text(const char *text, size_t len, int32_t grav, int32_t device,
                                                    astroz_constellation_t *out);
 
+/* Same, from numeric mean elements (the fields Tle.parseOmm fills from an OMM record, src/Tle.zig:134-215):
+ * epoch_jd, mean motion [rev/day], eccentricity, inclination / RAAN / argument of perigee / mean anomaly [deg],
+ * B* [1/earth radii].  No text round trip, so Monte-Carlo draws keep their full fp64 values. */
+int32_t astroz_cuda_constellation_create_from_elements(const double *epoch_jd, const double *mean_motion_rev_day,
+                                                       const double *ecc, const double *incl_deg, const double *raan_deg,
+                                                       const double *argp_deg, const double *ma_deg, const double *bstar,
+                                                       uint32_t n, int32_t grav, int32_t device,
+                                                       astroz_constellation_t *out);
+
 void astroz_cuda_constellation_free(astroz_constellation_t h);
 
 /* numSatellites / numSgp4 / numSdp4 (src/Constellation.zig:82,89,95) */

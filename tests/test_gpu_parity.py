@@ -422,3 +422,36 @@ def test_config5_monte_carlo_draws_and_fp32_study(az, oracle, synth):
         c.propagate_device_f32(jd, fr, p32, v32, phase64=phase)
         c.synchronize()
         assert float((p32 - p64).abs().max()) < tol
+
+
+def test_constellation_from_numeric_elements(az, oracle, synth):
+    """OMM-style ingest: numeric mean elements instead of TLE text (src/Tle.zig:134-215) give the same
+    constellation as the text route when fed the values the text encodes."""
+    tles = synth.mixed_catalog(120, n_geo=10, n_molniya=6, n_gps=4)
+    t = [oracle.parse_tle(*x) for x in tles]
+    cols = {k: np.array([r[k] for r in t]) for k in ("epochJd", "nRevDay", "ecc", "inclDeg", "raanDeg", "argpDeg", "maDeg", "bstar")}
+    a = az.Constellation(tles)
+    b = az.Constellation.from_elements(cols["epochJd"], cols["nRevDay"], cols["ecc"], cols["inclDeg"], cols["raanDeg"],
+                                       cols["argpDeg"], cols["maDeg"], cols["bstar"])
+    assert list(a.classes) == list(b.classes) and np.array_equal(a.epochs, b.epochs)
+    jd, fr = synth.time_grid(50)
+    pa, va = a.propagate(jd, fr, layout=0)
+    pb, vb = b.propagate(jd, fr, layout=0)
+    assert np.array_equal(pa, pb) and np.array_equal(va, vb)
+    with pytest.raises(az.AstrozCudaError) as ei:
+        az.Constellation.from_elements([2460400.5], [15.5], [1.2], [51.0], [0.0], [0.0], [0.0], [1e-4])
+    assert ei.value.code == -11   # eccentricity outside [0, 1): src/Sgp4.zig:111-113
+
+
+def test_constellation_from_text_blob(az):
+    """Tle.MultiIterator semantics (src/Tle.zig:103-132): 3-line sets with name lines, blank lines, CRLF, a
+    dangling line 1 and a short line are all tolerated; pairs are (1..., 2...) lines of >= 69 columns."""
+    text = ("ISS (ZARYA)\r\n" + G.ISS[0] + "\r\n" + G.ISS[1] + "\r\n\r\n"
+            "GEO SAT\n  " + G.GEO28626[0] + "  \n" + G.GEO28626[1] + "\n"
+            + G.SAT55909[0] + "\n"            # line 1 without its line 2: dropped when the next line 1 arrives
+            + G.SAT55910[0] + "\n" + G.SAT55910[1] + "\n"
+            "1 short line\n")
+    c = az.Constellation.from_text(text)
+    assert (c.numSatellites, c.numSgp4, c.numSdp4) == (3, 2, 1)
+    ref = az.Constellation([G.ISS, G.GEO28626, G.SAT55910])
+    assert np.array_equal(c.epochs, ref.epochs) and list(c.classes) == list(ref.classes)
