@@ -78,6 +78,10 @@ def lib() -> C.CDLL:
         "astroz_cuda_sgp4_propagate_into": (i32, [vp, dp, u32, dp, dp, dp, i32, C.c_double, i32]),
         "astroz_cuda_sgp4_propagate_into_device": (i32, [vp, dp, u32, dp, vp, vp, i32, C.c_double, i32, vp]),
         "astroz_cuda_sgp4_screen": (i32, [vp, dp, u32, dp, u32, C.c_double, C.c_double, dp, C.POINTER(u32)]),
+        "astroz_cuda_constellation_coarse_screen_device": (i32, [vp, vp, u32, u32, i32, C.c_double, vp, vp, vp, u32,
+                                                                 C.POINTER(C.c_uint64)]),
+        "astroz_cuda_sgp4_screen_all": (i32, [vp, dp, u32, dp, C.c_double, C.POINTER(u32), C.POINTER(u32), u32,
+                                              C.POINTER(C.c_uint64)]),
         "astroz_cuda_sgp4_init": (i32, [C.c_char_p, C.c_char_p, i32, i32, C.POINTER(vp)]),
         "astroz_cuda_sgp4_free": (None, [vp]),
         "astroz_cuda_sgp4_is_deep_space": (i32, [vp]),
@@ -106,7 +110,7 @@ EXPORTS = [
     "astroz_cuda_constellation_propagate_device_f32", "astroz_cuda_constellation_reset_carry",
     "astroz_cuda_constellation_synchronize", "astroz_cuda_constellation_last_kernel_ms",
     "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sgp4_screen",
-    "astroz_cuda_sgp4_init",
+    "astroz_cuda_constellation_coarse_screen_device", "astroz_cuda_sgp4_screen_all", "astroz_cuda_sgp4_init",
     "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch",
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",
     "astroz_cuda_fp64_peak",

@@ -244,6 +244,57 @@ class Constellation:
         return dist, tidx
 
 
+    def coarse_screen_device(self, positions, threshold: float, layout: int = Layout.timeMajor, valid_mask=None,
+                             max_results: int = 10_000_000):
+        """coarse_screen(positions, num_sats, threshold, valid_mask) (bindings/python/src/conjunction.zig:11-149) on a
+        DEVICE position block (torch CUDA tensor shaped by `layout`).  Returns (pairs[n, 2] uint32, t_indices[n]
+        uint32) as numpy arrays, sorted by (t, s, other); raises if more than max_results hits were found."""
+        import torch
+
+        shape = tuple(positions.shape)
+        ns, nt = (shape[0], shape[1]) if layout == Layout.satelliteMajor else (shape[1], shape[0])
+        dev = positions.device
+        pairs = torch.empty((max_results, 2), dtype=torch.int32, device=dev)
+        tidx = torch.empty((max_results,), dtype=torch.int32, device=dev)
+        cnt = C.c_uint64()
+        torch.cuda.synchronize(dev)
+        check(lib().astroz_cuda_constellation_coarse_screen_device(
+            self._h, C.c_void_p(positions.data_ptr()), ns, nt, int(layout), float(threshold),
+            C.c_void_p(valid_mask.data_ptr()) if valid_mask is not None else None,
+            C.c_void_p(pairs.data_ptr()), C.c_void_p(tidx.data_ptr()), max_results, C.byref(cnt)))
+        if cnt.value > max_results:
+            raise AstrozCudaError(-20, f"{cnt.value} hits exceed max_results={max_results}")
+        k = cnt.value
+        return _sorted_hits(pairs[:k].cpu().numpy().view(np.uint32), tidx[:k].cpu().numpy().view(np.uint32))
+
+    def screen_all(self, times, threshold: float = 10.0, epoch_offsets=None, max_results: int = 10_000_000):
+        """The all-vs-all branch of astroz.screen(source, times, threshold)
+        (bindings/python/astroz/__init__.py:535-650): propagate, keep the block in HBM, coarse-screen it there;
+        only the hits come back.  Returns (pairs[n, 2], t_indices[n]) sorted by (t, s, other)."""
+        times = as_f64(times)
+        ns = self.numSgp4
+        off = np.zeros(ns) if epoch_offsets is None else as_f64(epoch_offsets)[:ns].copy()
+        pairs = np.empty((max_results, 2), dtype=np.uint32)
+        tidx = np.empty(max_results, dtype=np.uint32)
+        cnt = C.c_uint64()
+        check(lib().astroz_cuda_sgp4_screen_all(
+            self._h, dptr(times), times.shape[0], dptr(off), float(threshold),
+            pairs.ctypes.data_as(C.POINTER(C.c_uint32)), tidx.ctypes.data_as(C.POINTER(C.c_uint32)), max_results,
+            C.byref(cnt)))
+        if cnt.value > max_results:
+            raise AstrozCudaError(-20, f"{cnt.value} hits exceed max_results={max_results}")
+        return _sorted_hits(pairs[:cnt.value], tidx[:cnt.value])
+
+
+def _sorted_hits(pairs: np.ndarray, tidx: np.ndarray):
+    """Deterministic order for the hit set: by epoch, then satellite, then partner (the reference's order up to
+    ties inside one satellite's neighbourhood walk)."""
+    if len(tidx) == 0:
+        return pairs.reshape(0, 2).copy(), tidx.copy()
+    order = np.lexsort((pairs[:, 1], pairs[:, 0], tidx))
+    return np.ascontiguousarray(pairs[order]), np.ascontiguousarray(tidx[order])
+
+
 def fp64_peak_tflops(device: int = 0) -> float:
     """Measured DFMA throughput of the device (the fp64 roofline denominator)."""
     v = C.c_double()

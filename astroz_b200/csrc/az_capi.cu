@@ -95,6 +95,9 @@ struct Constellation {
     int latticeNodes = 0;
     // staging for the host-buffer API
     DevBuf<double> dPos, dVel;
+    // coarse-screen scratch: hash heads / chains for one batch of epochs, hit buffers, counter
+    DevBuf<uint32_t> dHead, dNext, dPairs, dTIdx;
+    DevBuf<unsigned long long> dCount;
     // kernel timing
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t chunkDone[64] = {};
@@ -106,6 +109,7 @@ struct Constellation {
         cudaSetDevice(device);
         dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release();
         dSdp4.release(); dTime.release(); dToffCall.release(); dLattice.release(); dPos.release(); dVel.release();
+        dHead.release(); dNext.release(); dPairs.release(); dTIdx.release(); dCount.release();
         for (auto &h : hTimeSlot) if (h) cudaFreeHost(h);
         if (hToffCall) cudaFreeHost(hToffCall);
         for (auto &e : slotCopied) if (e) cudaEventDestroy(e);
@@ -811,6 +815,89 @@ int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, u
     AZ_CUDA(cudaMemcpyAsync(out_min_dists, a.minDist, (size_t)ns * 8, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemcpyAsync(out_min_t, a.minT, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
+    return ASTROZ_OK;
+}
+
+// ---- all-vs-all coarse screen ----------------------------------------------------------------------
+static int32_t coarse_screen_run(Constellation *c, const double *dPositions, uint32_t ns, uint32_t nt, int layout,
+                                 double threshold, const uint8_t *dMask, uint32_t *dPairs, uint32_t *dT,
+                                 uint32_t maxResults, uint64_t *count, cudaStream_t s) {
+    constexpr uint32_t kBits = 16, kBatch = 128;  // 128 epochs per pass: 32 MB of bucket heads
+    const uint32_t batch = std::min(kBatch, nt);
+    AZ_CUDA(c->dHead.reserve((size_t)batch << kBits));
+    AZ_CUDA(c->dNext.reserve((size_t)batch * ns));
+    AZ_CUDA(c->dCount.reserve(1));
+    AZ_CUDA(cudaMemsetAsync(c->dCount.p, 0, 8, s));
+    for (uint32_t t0 = 0; t0 < nt; t0 += batch) {
+        az::CoarseArgs a;
+        a.pos = dPositions;
+        a.validMask = dMask;
+        a.nSats = ns;
+        a.nTimes = nt;
+        a.layout = layout;
+        a.threshold = threshold;
+        a.t0 = t0;
+        a.tCount = std::min(batch, nt - t0);
+        a.tableBits = kBits;
+        a.head = c->dHead.p;
+        a.next = c->dNext.p;
+        a.pairs = dPairs;
+        a.tIdx = dT;
+        a.maxResults = maxResults;
+        a.count = c->dCount.p;
+        AZ_CUDA(az::launch_coarse_screen(a, s));
+    }
+    unsigned long long found = 0;
+    AZ_CUDA(cudaMemcpyAsync(&found, c->dCount.p, 8, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    *count = found;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_coarse_screen_device(astroz_constellation_t h, const double *d_positions,
+                                                       uint32_t num_sats, uint32_t num_times, int32_t layout,
+                                                       double threshold, const uint8_t *d_valid_mask, uint32_t *d_pairs,
+                                                       uint32_t *d_t_indices, uint32_t max_results, uint64_t *count) {
+    Constellation *c = static_cast<Constellation *>(h);
+    if (!c || !d_positions || !count || (max_results && (!d_pairs || !d_t_indices))) return ASTROZ_NULL_POINTER;
+    if (layout < 0 || layout > 1 || !(threshold > 0.0)) {
+        g_lastError = "coarse screen: layout must be 0/1 and threshold positive";
+        return ASTROZ_VALUE_ERROR;
+    }
+    *count = 0;
+    if (num_sats == 0 || num_times == 0) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    return coarse_screen_run(c, d_positions, num_sats, num_times, layout, threshold, d_valid_mask, d_pairs, d_t_indices,
+                             max_results, count, c->stream);
+}
+
+int32_t astroz_cuda_sgp4_screen_all(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                    const double *epoch_offsets, double threshold, uint32_t *pairs, uint32_t *t_indices,
+                                    uint32_t max_results, uint64_t *count) {
+    Constellation *c = static_cast<Constellation *>(h);
+    if (!c || !times || !epoch_offsets || !count || (max_results && (!pairs || !t_indices))) return ASTROZ_NULL_POINTER;
+    if (!(threshold > 0.0)) return ASTROZ_VALUE_ERROR;
+    *count = 0;
+    const uint32_t ns = c->cat.nSgp4;
+    if (ns == 0 || n_times == 0) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    AZ_CUDA(c->dPos.reserve((size_t)ns * n_times * 3));
+    // positions only, time-major: a warp of the screen kernels then reads 32 neighbouring satellites of one epoch
+    int32_t rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, nullptr, ASTROZ_MODE_TEME, 0.0,
+                                  ASTROZ_LAYOUT_TIME_MAJOR, s);
+    if (rc != ASTROZ_OK) return rc;
+    AZ_CUDA(c->dPairs.reserve((size_t)std::max<uint32_t>(max_results, 1) * 2));
+    AZ_CUDA(c->dTIdx.reserve(std::max<uint32_t>(max_results, 1)));
+    rc = coarse_screen_run(c, c->dPos.p, ns, n_times, ASTROZ_LAYOUT_TIME_MAJOR, threshold, nullptr, c->dPairs.p,
+                           c->dTIdx.p, max_results, count, s);
+    if (rc != ASTROZ_OK) return rc;
+    const size_t stored = (size_t)std::min<uint64_t>(*count, max_results);
+    if (stored) {
+        AZ_CUDA(cudaMemcpyAsync(pairs, c->dPairs.p, stored * 8, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaMemcpyAsync(t_indices, c->dTIdx.p, stored * 4, cudaMemcpyDeviceToHost, s));
+        AZ_CUDA(cudaStreamSynchronize(s));
+    }
     return ASTROZ_OK;
 }
 

@@ -621,6 +621,98 @@ cudaError_t launch_sgp4_screen(const ScreenArgs &a, cudaStream_t stream) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K4: coarse all-vs-all screen (bindings/python/src/conjunction.zig:11-149).  Same cell list and the same
+// multiplicative hash as the reference; differences: the table is built with atomicExch (chain order is
+// irrelevant to the result set), cell coordinates of a chain member are recomputed from its position
+// instead of stored, and only the own cell + 13 lexicographically-forward neighbours are visited -- each
+// cross-cell pair is met exactly once from the side whose offset is forward, same-cell pairs by other > s --
+// instead of 27 cells with an other > s filter.  Output order is not the reference's (by epoch, then by
+// satellite): callers get the same SET of (s, other, t) triples.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint32_t kCoarseEmpty = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t spatial_hash(int cx, int cy, int cz) {  // conjunction.zig:139-148
+    uint32_t h = (uint32_t)cx;
+    h *= 2654435761u;
+    h ^= (uint32_t)cy;
+    h *= 2654435761u;
+    h ^= (uint32_t)cz;
+    h *= 2654435761u;
+    return h;
+}
+
+__device__ __forceinline__ const double *coarse_pos(const CoarseArgs &a, uint32_t s, uint32_t t) {
+    return a.pos + ((a.layout == 0) ? ((size_t)s * a.nTimes + t) * 3 : ((size_t)t * a.nSats + s) * 3);
+}
+
+__global__ void __launch_bounds__(256) coarse_build_kernel(const CoarseArgs a) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.nSats) return;
+    const uint32_t tb = blockIdx.y, t = a.t0 + tb;
+    if (a.validMask && a.validMask[s] == 0) return;
+    const double *p = coarse_pos(a, s, t);
+    const double x = __ldg(p);
+    if (!isfinite(x)) return;  // conjunction.zig:60-63
+    const double inv = 1.0 / a.threshold;
+    const int cx = (int)floor(x * inv), cy = (int)floor(__ldg(p + 1) * inv), cz = (int)floor(__ldg(p + 2) * inv);
+    const uint32_t h = spatial_hash(cx, cy, cz) & ((1u << a.tableBits) - 1u);
+    a.next[(size_t)tb * a.nSats + s] = atomicExch(a.head + ((size_t)tb << a.tableBits) + h, s);
+}
+
+__global__ void __launch_bounds__(256) coarse_pairs_kernel(const CoarseArgs a) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= a.nSats) return;
+    const uint32_t tb = blockIdx.y, t = a.t0 + tb;
+    if (a.validMask && a.validMask[s] == 0) return;
+    const double *p = coarse_pos(a, s, t);
+    const double sx = __ldg(p);
+    if (!isfinite(sx)) return;
+    const double sy = __ldg(p + 1), sz = __ldg(p + 2);
+    const double inv = 1.0 / a.threshold, thr2 = a.threshold * a.threshold;
+    const int scx = (int)floor(sx * inv), scy = (int)floor(sy * inv), scz = (int)floor(sz * inv);
+    const uint32_t mask = (1u << a.tableBits) - 1u;
+    const uint32_t *head = a.head + ((size_t)tb << a.tableBits);
+    const uint32_t *next = a.next + (size_t)tb * a.nSats;
+#pragma unroll 1
+    for (int n = 13; n < 27; ++n) {  // offsets (dx,dy,dz) in lexicographic order: index 13 is (0,0,0), 14..26 are forward
+        const int dx = n / 9 - 1, dy = (n / 3) % 3 - 1, dz = n % 3 - 1;
+        const int ncx = scx + dx, ncy = scy + dy, ncz = scz + dz;
+        uint32_t idx = __ldg(head + (spatial_hash(ncx, ncy, ncz) & mask));
+        while (idx != kCoarseEmpty) {
+            const uint32_t other = idx;
+            idx = __ldg(next + other);
+            if (other == s || (n == 13 && other < s)) continue;
+            if (a.validMask && a.validMask[other] == 0) continue;
+            const double *q = coarse_pos(a, other, t);
+            const double ox = __ldg(q), oy = __ldg(q + 1), oz = __ldg(q + 2);
+            if ((int)floor(ox * inv) != ncx || (int)floor(oy * inv) != ncy || (int)floor(oz * inv) != ncz)
+                continue;  // hash collision: another cell in the same bucket (conjunction.zig:112-113)
+            const double ddx = sx - ox, ddy = sy - oy, ddz = sz - oz;
+            if (ddx * ddx + ddy * ddy + ddz * ddz < thr2) {
+                const unsigned long long k = atomicAdd(a.count, 1ULL);
+                if (k < a.maxResults) {
+                    a.pairs[2 * k] = min(s, other);
+                    a.pairs[2 * k + 1] = max(s, other);
+                    a.tIdx[k] = t;
+                }
+            }
+        }
+    }
+}
+
+cudaError_t launch_coarse_screen(const CoarseArgs &a, cudaStream_t stream) {
+    if (a.nSats == 0 || a.tCount == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.head, 0xff, ((size_t)a.tCount << a.tableBits) * 4, stream);
+    if (e != cudaSuccess) return e;
+    dim3 grid((a.nSats + 255) / 256, a.tCount);
+    coarse_build_kernel<<<grid, 256, 0, stream>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    coarse_pairs_kernel<<<grid, 256, 0, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------
 // fp32 precision-study kernel (BASELINE config 5; no reference path).  Same mapping as K1.
 // ---------------------------------------------------------------------------------------------------
 template <bool kPhase64>

@@ -70,6 +70,26 @@ struct ScreenArgs {
 };
 cudaError_t launch_sgp4_screen(const ScreenArgs &a, cudaStream_t stream);
 
+// K4: all-vs-all coarse conjunction screen over a device-resident position block
+// (bindings/python/src/conjunction.zig:11-149): per epoch a cell list (cell edge = threshold) in a hash table,
+// then each satellite checks its own and 13 forward neighbour cells.
+struct CoarseArgs {
+    const double *pos = nullptr;       // [nSats][nTimes][3] (layout 0) or [nTimes][nSats][3] (layout 1)
+    const uint8_t *validMask = nullptr;  // nullable, per satellite
+    uint32_t nSats = 0, nTimes = 0;
+    int layout = 1;
+    double threshold = 0.0;
+    uint32_t t0 = 0, tCount = 0;       // epoch batch handled by this launch pair
+    uint32_t tableBits = 16;
+    uint32_t *head = nullptr;          // [tCount][1 << tableBits]
+    uint32_t *next = nullptr;          // [tCount][nSats]
+    uint32_t *pairs = nullptr;         // [maxResults][2]
+    uint32_t *tIdx = nullptr;          // [maxResults]
+    uint32_t maxResults = 0;
+    unsigned long long *count = nullptr;  // device counter (total hits, may exceed maxResults)
+};
+cudaError_t launch_coarse_screen(const CoarseArgs &a, cudaStream_t stream);
+
 // fp32 study kernel (BASELINE config 5): same grid / layout as K1 (satellite-major TEME, fp64 output words),
 // arithmetic in fp32; phase64 != 0 forms the secular angles in fp64 first.
 cudaError_t launch_sgp4_grid_f32(const GridArgs &a, int phase64, cudaStream_t stream);

@@ -163,6 +163,26 @@ int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, u
                                 const double *epoch_offsets, uint32_t target_idx, double threshold,
                                 double reference_jd, double *out_min_dists, uint32_t *out_min_t);
 
+/* All-vs-all coarse conjunction screen: replaces coarse_screen / coarseScreen
+ * (bindings/python/src/conjunction.zig:11-149).  d_positions: DEVICE block (num_sats, num_times, 3) for
+ * layout 0 or (num_times, num_sats, 3) for layout 1 (e.g. left in HBM by *_propagate_device);
+ * d_valid_mask: nullable per-satellite bytes.  Every (s, other, t) with s < other closer than `threshold`
+ * at epoch t is appended to d_pairs[2k], d_pairs[2k+1], d_t_indices[k] (device buffers of max_results
+ * entries; order unspecified -- the reference emits the same set ordered by epoch).  *count receives the
+ * number of hits found, which may exceed max_results (then only max_results were stored).  Synchronous. */
+int32_t astroz_cuda_constellation_coarse_screen_device(astroz_constellation_t h, const double *d_positions,
+                                                       uint32_t num_sats, uint32_t num_times, int32_t layout,
+                                                       double threshold, const uint8_t *d_valid_mask, uint32_t *d_pairs,
+                                                       uint32_t *d_t_indices, uint32_t max_results, uint64_t *count);
+
+/* The all-vs-all branch of astroz.screen(source, times, threshold) (bindings/python/astroz/__init__.py:535-650):
+ * propagate the near-earth satellites (tsince = times[t] + epoch_offsets[sat], TEME, positions only), keep the
+ * block in HBM, run the coarse screen on it, return only the hits.  pairs / t_indices: HOST buffers of
+ * max_results entries. */
+int32_t astroz_cuda_sgp4_screen_all(astroz_constellation_t h, const double *times, uint32_t n_times,
+                                    const double *epoch_offsets, double threshold, uint32_t *pairs, uint32_t *t_indices,
+                                    uint32_t max_results, uint64_t *count);
+
 /* block until everything queued on the handle's stream has finished */
 int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h);
 

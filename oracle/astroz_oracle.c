@@ -1169,3 +1169,72 @@ done:
     free(el);
     return rc;
 }
+
+/* ------------------------------------------------------------------ conjunction.zig:11-149 */
+static uint32_t spatial_hash(int32_t cx, int32_t cy, int32_t cz) { /* conjunction.zig:139-148 */
+    uint32_t h = (uint32_t)cx;
+    h *= 2654435761u;
+    h ^= (uint32_t)cy;
+    h *= 2654435761u;
+    h ^= (uint32_t)cz;
+    h *= 2654435761u;
+    return h;
+}
+
+size_t azo_coarse_screen(const double *positions, size_t num_sats, size_t num_times, double threshold,
+                         const uint8_t *valid_mask, uint32_t *out_pairs, uint32_t *out_t, size_t max_results) {
+    const double inv_cell = 1.0 / threshold, thr2 = threshold * threshold;
+    const size_t TABLE = 1u << 16;
+    const uint32_t MASK = (uint32_t)TABLE - 1u, EMPTY = 0xffffffffu;
+    size_t count = 0;
+    int32_t *cx = (int32_t *)malloc(sizeof(int32_t) * num_sats * 3);
+    int32_t *cy = cx + num_sats, *cz = cx + 2 * num_sats;
+    uint32_t *hashes = (uint32_t *)malloc(sizeof(uint32_t) * num_sats);
+    uint32_t *head = (uint32_t *)malloc(sizeof(uint32_t) * TABLE);
+    uint32_t *next = (uint32_t *)malloc(sizeof(uint32_t) * num_sats);
+    for (size_t t = 0; t < num_times; t++) {
+        memset(head, 0xff, sizeof(uint32_t) * TABLE);
+        for (size_t s = 0; s < num_sats; s++) {
+            if (valid_mask && valid_mask[s] == 0) { hashes[s] = EMPTY; continue; }
+            size_t base = s * num_times * 3 + t * 3;
+            double x = positions[base];
+            if (!isfinite(x)) { hashes[s] = EMPTY; continue; }
+            cx[s] = (int32_t)floor(x * inv_cell);
+            cy[s] = (int32_t)floor(positions[base + 1] * inv_cell);
+            cz[s] = (int32_t)floor(positions[base + 2] * inv_cell);
+            uint32_t h = spatial_hash(cx[s], cy[s], cz[s]) & MASK;
+            hashes[s] = h;
+            next[s] = head[h];
+            head[h] = (uint32_t)s;
+        }
+        for (size_t s = 0; s < num_sats; s++) {
+            if (hashes[s] == EMPTY) continue;
+            size_t bs = s * num_times * 3 + t * 3;
+            double sx = positions[bs], sy = positions[bs + 1], sz = positions[bs + 2];
+            for (int dx = -1; dx <= 1; dx++)
+                for (int dy = -1; dy <= 1; dy++)
+                    for (int dz = -1; dz <= 1; dz++) {
+                        int32_t ncx = cx[s] + dx, ncy = cy[s] + dy, ncz = cz[s] + dz;
+                        uint32_t idx = head[spatial_hash(ncx, ncy, ncz) & MASK];
+                        while (idx != EMPTY) {
+                            uint32_t other = idx;
+                            idx = next[idx];
+                            if (other <= s) continue;
+                            if (cx[other] != ncx || cy[other] != ncy || cz[other] != ncz) continue;
+                            size_t bo = (size_t)other * num_times * 3 + t * 3;
+                            double ddx = sx - positions[bo], ddy = sy - positions[bo + 1], ddz = sz - positions[bo + 2];
+                            if (ddx * ddx + ddy * ddy + ddz * ddz < thr2) {
+                                if (count >= max_results) goto done;
+                                out_pairs[count * 2] = (uint32_t)s;
+                                out_pairs[count * 2 + 1] = other;
+                                out_t[count] = (uint32_t)t;
+                                count++;
+                            }
+                        }
+                    }
+        }
+    }
+done:
+    free(cx); free(hashes); free(head); free(next);
+    return count;
+}

@@ -115,6 +115,11 @@ int azo_screen_constellation(const char *const *lines1, const char *const *lines
                              const double *times, size_t nt, const double *epoch_offsets, size_t target_idx,
                              double threshold, double reference_jd, double *out_min_dists, uint32_t *out_min_t);
 
+/* coarseScreen (bindings/python/src/conjunction.zig:11-149): satellite-major positions [num_sats][num_times][3],
+ * cell-list spatial hash per time step.  Returns the number of results written (<= max_results). */
+size_t azo_coarse_screen(const double *positions, size_t num_sats, size_t num_times, double threshold,
+                         const uint8_t *valid_mask, uint32_t *out_pairs, uint32_t *out_t_indices, size_t max_results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,9 @@ def lib() -> C.CDLL:
             C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int, dp, C.c_size_t, dp, C.c_size_t,
             C.c_double, C.c_double, dp, C.POINTER(C.c_uint32)]
         L.azo_screen_constellation.restype = C.c_int
+        L.azo_coarse_screen.argtypes = [dp, C.c_size_t, C.c_size_t, C.c_double, C.POINTER(C.c_uint8),
+                                        C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_size_t]
+        L.azo_coarse_screen.restype = C.c_size_t
         _lib = L
     return _lib
 
@@ -238,6 +241,23 @@ def screen_constellation(tles, times, epoch_offsets, target: int, threshold: flo
     if rc != 0:
         raise ValueError(f"oracle screen failed rc={rc}")
     return dist, tidx
+
+
+def coarse_screen(positions_sat_major, threshold: float, valid_mask=None, max_results: int = 10_000_000):
+    """Oracle of coarseScreen (bindings/python/src/conjunction.zig:11-149) on a (n_sats, n_times, 3) block.
+    Returns (pairs[n, 2], t_indices[n]) sorted by (t, s, other)."""
+    pos = np.ascontiguousarray(positions_sat_major, dtype=np.float64)
+    ns, nt = pos.shape[0], pos.shape[1]
+    pairs = np.zeros((max_results, 2), dtype=np.uint32)
+    tidx = np.zeros(max_results, dtype=np.uint32)
+    m = None if valid_mask is None else np.ascontiguousarray(valid_mask, dtype=np.uint8)
+    k = lib().azo_coarse_screen(_dp(pos), ns, nt, float(threshold),
+                                m.ctypes.data_as(C.POINTER(C.c_uint8)) if m is not None else None,
+                                pairs.ctypes.data_as(C.POINTER(C.c_uint32)), tidx.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                max_results)
+    pairs, tidx = pairs[:k], tidx[:k]
+    order = np.lexsort((pairs[:, 1], pairs[:, 0], tidx)) if k else np.zeros(0, dtype=np.int64)
+    return pairs[order], tidx[order]
 
 
 # ---------------------------------------------------------------------------------------------------

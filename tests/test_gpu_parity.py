@@ -455,3 +455,43 @@ def test_constellation_from_text_blob(az):
     assert (c.numSatellites, c.numSgp4, c.numSdp4) == (3, 2, 1)
     ref = az.Constellation([G.ISS, G.GEO28626, G.SAT55910])
     assert np.array_equal(c.epochs, ref.epochs) and list(c.classes) == list(ref.classes)
+
+
+def test_all_vs_all_coarse_screen(az, oracle, synth):
+    """coarseScreen (bindings/python/src/conjunction.zig:11-149) on the device: same SET of (s, other, t) hits as
+    the CPU cell list, both on an externally supplied block (either layout, with a mask and NaN rows) and
+    through the fused propagate -> screen entry point."""
+    import torch
+
+    tles = synth.near_earth_catalog(900)
+    base = tles[7]
+    for k in range(10):       # a cluster of near-neighbours so there are hits at a 30 km threshold
+        l2 = base[1]
+        ma = (float(l2[43:51]) + 0.05 * (k + 1)) % 360.0
+        l2 = l2[:43] + f"{ma:8.4f}" + l2[51:68]
+        tles[200 + 3 * k] = (base[0], l2 + str(synth._checksum(l2)))
+    c = az.Constellation(tles)
+    times = np.arange(0.0, 360.0, 1.5)
+    ref = 2460437.5
+    off = (ref - c.epochs) * 1440.0
+    p_tm, _ = c.propagate_into(times, epoch_offsets=off, want_velocities=False, time_major=True)
+    p_sm = np.ascontiguousarray(p_tm.transpose(1, 0, 2))
+    thr = 30.0
+    want_pairs, want_t = oracle.coarse_screen(p_sm, thr)
+    assert len(want_t) > 50
+    got_pairs, got_t = c.screen_all(times, thr, epoch_offsets=off)
+    assert np.array_equal(got_pairs, want_pairs) and np.array_equal(got_t, want_t)
+    # external block, satellite-major, with a masked satellite and a NaN row
+    dev = torch.device("cuda", 0)
+    blk = p_sm.copy()
+    blk[203] = np.nan
+    mask = np.ones(900, dtype=np.uint8)
+    mask[206] = 0
+    w_pairs, w_t = oracle.coarse_screen(blk, thr, valid_mask=mask)
+    g_pairs, g_t = c.coarse_screen_device(torch.as_tensor(blk, device=dev), thr, layout=0,
+                                          valid_mask=torch.as_tensor(mask, device=dev))
+    assert np.array_equal(g_pairs, w_pairs) and np.array_equal(g_t, w_t)
+    assert not np.isin(203, g_pairs) and not np.isin(206, g_pairs)
+    g2_pairs, g2_t = c.coarse_screen_device(torch.as_tensor(np.ascontiguousarray(blk.transpose(1, 0, 2)), device=dev),
+                                            thr, layout=1, valid_mask=torch.as_tensor(mask, device=dev))
+    assert np.array_equal(g2_pairs, w_pairs) and np.array_equal(g2_t, w_t)

@@ -12,3 +12,10 @@ for _ in range(K): d, ti = c.screen_conjunction(times, 0, 10.0, epoch_offsets=of
 dt = (time.perf_counter() - t0) / K
 print(json.dumps({"screen_e2e_ms": dt * 1e3, "cells": len(tles) * len(times), "Gprops_e2e": len(tles) * len(times) / dt / 1e9,
                   "kernel_ms": c.last_kernel_ms()[0], "below_threshold": int((d < 10.0).sum())}))
+
+for _ in range(2): pairs, ti = c.screen_all(times, 10.0, epoch_offsets=off)
+t0 = time.perf_counter(); K = 5
+for _ in range(K): pairs, ti = c.screen_all(times, 10.0, epoch_offsets=off)
+dt = (time.perf_counter() - t0) / K
+print(json.dumps({"screen_all_e2e_ms": dt * 1e3, "Gprops_e2e": len(tles) * len(times) / dt / 1e9, "hits": int(len(ti)),
+                  "what": "all-vs-all: propagate (positions, time-major) + device cell-list screen, hits only come back"}))
