@@ -117,7 +117,12 @@ __device__ __forceinline__ void emit_run_sat_major(const GridArgs &a, uint32_t r
     }
     __syncwarp();
     const size_t base = ((size_t)row * a.nTimes + tw) * 3;  // in doubles; src/Constellation.zig:46-51
-    const bool vec = (count == 32) && ((base & 1) == 0);   // 16-byte aligned full run
+    // 128-bit path only for a full run whose destination is 16-byte aligned in every target mapping (the
+    // mappings share their alignment: symmetric allocations, and the caller's row/epoch shift is common)
+    const double *probe = (kGather == 1) ? a.mcPos : (kGather == 2 ? a.peerPos[0] : a.pos);
+    const bool vec = (count == 32) && ((reinterpret_cast<uintptr_t>(probe + base) & 15u) == 0) &&
+                     (!kVel || ((reinterpret_cast<uintptr_t>((kGather == 1) ? a.mcVel : (kGather == 2 ? a.peerVel[0] : a.vel)) & 15u) ==
+                                (reinterpret_cast<uintptr_t>(probe) & 15u)));
 #pragma unroll
     for (int which = 0; which < (kVel ? 2 : 1); ++which) {
         const double *src = stage + which * kStageDoubles;
@@ -186,7 +191,9 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
         const uint32_t sat0 = tileIdx * kTileSats;
         const uint32_t row0 = __ldg(a.orig + sat0);
         const uint32_t nReal = min((uint32_t)kTileSats, a.nSats - sat0);
-        bool block8 = nReal == kTileSats && ((((size_t)a.outNumSats * 3) & 1) == 0) && ((row0 * 3u) & 1u) == 0;
+        bool block8 = nReal == kTileSats && ((((size_t)a.outNumSats * 3) & 1) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(a.pos + (size_t)row0 * 3) & 15u) == 0) &&
+                      (!kVel || (reinterpret_cast<uintptr_t>(a.vel + (size_t)row0 * 3) & 15u) == 0);
 #pragma unroll
         for (int k = 1; k < kTileSats; ++k) block8 = block8 && (k >= (int)nReal || __ldg(a.orig + sat0 + k) == row0 + k);
 #pragma unroll 1

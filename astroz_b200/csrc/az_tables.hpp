@@ -5,8 +5,10 @@
 // src/Constellation.zig:101-200.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "az_device.cuh"
@@ -78,27 +80,66 @@ inline int build_catalog_records(const TleRecord *recs, uint32_t n, int gravSel,
     out.grav = gravity(gravSel);
     out.epochs.resize(n);
     out.classes.resize(n);
+
+    // Element initialisation is embarrassingly parallel and ~0.6 us per satellite on one core; large ingests
+    // (Monte-Carlo draws, OMM streams) are cut into contiguous chunks, one host thread each, and concatenated in
+    // chunk order so the catalog order -- and with it the reference epoch and every output row -- is unchanged.
+    struct Chunk {
+        std::vector<NearEarth> near;
+        std::vector<uint32_t> nearIdx;
+        std::vector<Sdp4Sat> deep;
+        std::vector<uint32_t> deepIdx;
+        int rc = kOk;
+        uint32_t failAt = 0xffffffffu;
+    };
+    uint32_t nThreads = 1;
+    if (n >= 20000) nThreads = std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), std::min<uint32_t>(64, n / 5000));
+    std::vector<Chunk> chunks(nThreads);
+    auto work = [&](uint32_t k) {
+        Chunk &c = chunks[k];
+        const uint32_t b = (uint32_t)((uint64_t)n * k / nThreads), e = (uint32_t)((uint64_t)n * (k + 1) / nThreads);
+        c.near.reserve(e - b);
+        c.nearIdx.reserve(e - b);
+        for (uint32_t i = b; i < e; ++i) {
+            const TleRecord &t = recs[i];
+            out.epochs[i] = t.epochJd;
+            NearEarth ne;
+            int rc = build_near_earth(t, out.grav, ne);
+            if (rc == kOk) {
+                c.near.push_back(ne);
+                c.nearIdx.push_back(i);
+                out.classes[i] = 0;
+            } else if (rc == kDeepSpace) {
+                DeepSpace ds;
+                rc = build_deep_space(t, out.grav, ds);
+                if (rc != kOk) { c.rc = rc; c.failAt = i; return; }
+                c.deep.push_back(sdp4_record(ds));
+                c.deepIdx.push_back(i);
+                out.classes[i] = 1 + ds.irez;
+            } else {
+                c.rc = rc;
+                c.failAt = i;
+                return;
+            }
+        }
+    };
+    if (nThreads == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> pool;
+        for (uint32_t k = 0; k < nThreads; ++k) pool.emplace_back(work, k);
+        for (auto &th : pool) th.join();
+    }
+    for (const Chunk &c : chunks)  // the first failing element set (in catalog order) aborts, like the reference
+        if (c.rc != kOk) return c.rc;
     std::vector<NearEarth> near;
     near.reserve(n);
-    for (uint32_t i = 0; i < n; ++i) {
-        const TleRecord &t = recs[i];
-        out.epochs[i] = t.epochJd;
-        NearEarth ne;
-        int rc = build_near_earth(t, out.grav, ne);
-        if (rc == kOk) {
-            near.push_back(ne);
-            out.sgp4Orig.push_back(i);
-            out.classes[i] = 0;
-        } else if (rc == kDeepSpace) {
-            DeepSpace ds;
-            rc = build_deep_space(t, out.grav, ds);
-            if (rc != kOk) return rc;
-            out.sdp4.push_back(sdp4_record(ds));
-            out.sdp4Orig.push_back(i);
-            out.classes[i] = 1 + ds.irez;
-        } else {
-            return rc;
-        }
+    for (Chunk &c : chunks) {
+        near.insert(near.end(), c.near.begin(), c.near.end());
+        out.sgp4Orig.insert(out.sgp4Orig.end(), c.nearIdx.begin(), c.nearIdx.end());
+        out.sdp4.insert(out.sdp4.end(), c.deep.begin(), c.deep.end());
+        out.sdp4Orig.insert(out.sdp4Orig.end(), c.deepIdx.begin(), c.deepIdx.end());
+        Chunk().near.swap(c.near);
     }
     out.nSgp4 = (uint32_t)near.size();
     out.nSdp4 = (uint32_t)out.sdp4.size();

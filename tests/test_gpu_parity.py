@@ -495,3 +495,27 @@ def test_all_vs_all_coarse_screen(az, oracle, synth):
     g2_pairs, g2_t = c.coarse_screen_device(torch.as_tensor(np.ascontiguousarray(blk.transpose(1, 0, 2)), device=dev),
                                             thr, layout=1, valid_mask=torch.as_tensor(mask, device=dev))
     assert np.array_equal(g2_pairs, w_pairs) and np.array_equal(g2_t, w_t)
+
+
+def test_odd_offsets_and_strides_take_the_unaligned_paths(az, synth):
+    """Output rows placed at an odd offset inside a larger block, odd epoch counts, odd row counts: the 128-bit
+    store paths must fall back to 8-byte stores (no misaligned access) and give the same numbers."""
+    import torch
+
+    tles = synth.near_earth_catalog(41)
+    c = az.Constellation(tles)
+    dev = torch.device("cuda", 0)
+    for nt in (97, 64):
+        jd, fr = synth.time_grid(nt)
+        ref_p, ref_v = c.propagate(jd, fr, layout=0)
+        for layout in (0, 1):
+            rows = 41 + 7
+            shape = (rows, nt, 3) if layout == 0 else (nt, rows, 3)
+            pos = torch.full(shape, -1.0, dtype=torch.float64, device=dev)
+            vel = torch.full(shape, -1.0, dtype=torch.float64, device=dev)
+            c.propagate_device(jd, fr, pos, vel, None, 0, layout, out_num_sats=rows, out_sat_offset=3)
+            c.synchronize()
+            p = pos.cpu().numpy() if layout == 0 else pos.cpu().numpy().transpose(1, 0, 2)
+            v = vel.cpu().numpy() if layout == 0 else vel.cpu().numpy().transpose(1, 0, 2)
+            assert np.array_equal(p[3:44], ref_p) and np.array_equal(v[3:44], ref_v)
+            assert np.all(p[:3] == -1.0) and np.all(p[44:] == -1.0)     # neighbours untouched
