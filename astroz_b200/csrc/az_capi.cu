@@ -172,6 +172,7 @@ int32_t finish_create(Constellation *c, int device) {
         AZ_CUDA(cudaMemcpy(c->dSdp4Orig.p, t.sdp4Orig.data(), t.nSdp4 * 4, cudaMemcpyHostToDevice));
     }
     if (const char *v = std::getenv("ASTROZ_SGP4_VARIANT")) c->variant = std::atoi(v);
+    if (const char *v = std::getenv("ASTROZ_SDP4_VARIANT")) az::set_sdp4_variant(std::atoi(v));
     if (const char *v = std::getenv("ASTROZ_D2H_CHUNKS")) c->chunks = std::max(1, std::min(64, std::atoi(v)));
     return ASTROZ_OK;
 }

@@ -456,8 +456,8 @@ cudaError_t launch_sdp4_lattice(const Sdp4Sat *sats, uint32_t nSats, double2 *la
 constexpr int kSdp4Threads = 128;
 constexpr int kSdp4Stripe = 512;
 
-template <int kLayout, int kMode, bool kVel, int kGather>
-__global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridArgs a) {
+template <int kLayout, int kMode, bool kVel, int kGather, int kMinBlocks>
+__global__ void __launch_bounds__(kSdp4Threads, kMinBlocks) sdp4_grid_kernel(const GridArgs a) {
     __shared__ Sdp4Sat e;
     __shared__ __align__(16) double stageAll[kGather != 0 ? (kSdp4Threads / 32) * 2 * kStageDoubles : 2];
     const uint32_t sat = blockIdx.x;
@@ -506,12 +506,23 @@ __global__ void __launch_bounds__(kSdp4Threads, 3) sdp4_grid_kernel(const GridAr
     }
 }
 
+#ifndef AZ_DEFAULT_K2_BLOCKS
+#define AZ_DEFAULT_K2_BLOCKS 5
+#endif
+static int g_k2Variant = -1;  // tuning only (ASTROZ_SDP4_VARIANT): 0 -> 3, 1 -> 4, 2 -> 5 resident CTAs per SM
+void set_sdp4_variant(int v) { g_k2Variant = v; }
+
 template <int kLayout, int kMode, bool kVel, int kGather = 0>
 static cudaError_t launch_k2(const GridArgs &a, cudaStream_t stream) {
     const uint32_t stripes = (a.nTimes + kSdp4Stripe - 1) / kSdp4Stripe;
     if (a.nSats == 0 || stripes == 0) return cudaSuccess;
     dim3 grid(a.nSats, stripes);
-    sdp4_grid_kernel<kLayout, kMode, kVel, kGather><<<grid, kSdp4Threads, 0, stream>>>(a);
+    if (kLayout == 0 && kMode == 0 && kVel && kGather == 0 && g_k2Variant >= 0) {
+        if (g_k2Variant == 1) { sdp4_grid_kernel<0, 0, true, 0, 4><<<grid, kSdp4Threads, 0, stream>>>(a); return cudaGetLastError(); }
+        if (g_k2Variant == 2) { sdp4_grid_kernel<0, 0, true, 0, 5><<<grid, kSdp4Threads, 0, stream>>>(a); return cudaGetLastError(); }
+        if (g_k2Variant == 0) { sdp4_grid_kernel<0, 0, true, 0, 3><<<grid, kSdp4Threads, 0, stream>>>(a); return cudaGetLastError(); }
+    }
+    sdp4_grid_kernel<kLayout, kMode, kVel, kGather, AZ_DEFAULT_K2_BLOCKS><<<grid, kSdp4Threads, 0, stream>>>(a);
     return cudaGetLastError();
 }
 

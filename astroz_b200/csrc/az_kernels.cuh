@@ -98,6 +98,7 @@ cudaError_t launch_sgp4_grid_f32(const GridArgs &a, int phase64, cudaStream_t st
 cudaError_t measure_fp64_peak(double *flops);
 
 int sgp4_variant_count();
+void set_sdp4_variant(int v);
 const char *sgp4_variant_name(int variant);
 
 }  // namespace az
