@@ -75,8 +75,8 @@ def lib() -> C.CDLL:
         "astroz_cuda_constellation_reset_carry": (i32, [vp]),
         "astroz_cuda_constellation_synchronize": (i32, [vp]),
         "astroz_cuda_constellation_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
-        "astroz_cuda_sgp4_propagate_into": (i32, [vp, dp, u32, dp, dp, dp, i32, C.c_double, i32]),
-        "astroz_cuda_sgp4_propagate_into_device": (i32, [vp, dp, u32, dp, vp, vp, i32, C.c_double, i32, vp]),
+        "astroz_cuda_sgp4_propagate_into": (i32, [vp, dp, u32, dp, dp, dp, i32, C.c_double, i32, vp, u32]),
+        "astroz_cuda_sgp4_propagate_into_device": (i32, [vp, dp, u32, dp, vp, vp, i32, C.c_double, i32, vp, u32, vp]),
         "astroz_cuda_sgp4_screen": (i32, [vp, dp, u32, dp, u32, C.c_double, C.c_double, dp, C.POINTER(u32)]),
         "astroz_cuda_constellation_coarse_screen_device": (i32, [vp, vp, u32, u32, i32, C.c_double, vp, vp, vp, u32,
                                                                  C.POINTER(C.c_uint64)]),

@@ -206,27 +206,34 @@ class Constellation:
         return float(ms[0]), float(ms[1]), float(ms[2])
 
     # ---- stateless near-earth path (Constellation.propagateConstellation, :541-605) -----------------
-    def propagate_into(self, times, positions=None, velocities=None, epoch_offsets=None,
+    def propagate_into(self, times, positions=None, velocities=None, epoch_offsets=None, satellite_mask=None,
                        outputMode: int = OutputMode.teme, reference_jd: float = 0.0, time_major: bool = True,
-                       want_velocities: bool = True):
-        """SatrecArray.propagate_into(times, positions, velocities, epoch_offsets=...)
-        (bindings/python/src/satrec.zig:896-988): tsince = times[t] + epoch_offsets[sat] for the
-        near-earth satellites only, written time-major (n_times, n_sgp4, 3) by default."""
+                       output_stride: int = -1, want_velocities: bool = True):
+        """Sgp4Constellation.propagate_into(times, positions, velocities, epoch_offsets=, satellite_mask=, output=,
+        reference_jd=, time_major=, output_stride=) (bindings/python/src/sgp4.zig:171-268): tsince = times[t] +
+        epoch_offsets[sat] for the near-earth satellites only, satellite i -> row i of a block with `output_stride`
+        rows (default: the number of near-earth satellites); rows whose mask byte is 0 are left untouched."""
         times = as_f64(times)
         nt = times.shape[0]
         ns = self.numSgp4
+        rows = ns if output_stride is None or output_stride <= 0 else int(output_stride)
         off = np.zeros(ns) if epoch_offsets is None else as_f64(epoch_offsets)[:ns].copy()
         layout = Layout.timeMajor if time_major else Layout.satelliteMajor
-        shape = self._shape(nt, layout, rows=ns)
+        shape = self._shape(nt, layout, rows=rows)
         if positions is None:
             positions = _lib.pinned_empty(shape)
         if velocities is None and want_velocities:
             velocities = _lib.pinned_empty(shape)
+        mask = None
+        if satellite_mask is not None:
+            mask = np.ascontiguousarray(satellite_mask, dtype=np.uint8)
+            if mask.shape[0] < ns:
+                raise ValueError("satellite_mask must have at least num_satellites elements")  # sgp4.zig:167
         check(lib().astroz_cuda_sgp4_propagate_into(
             self._h, dptr(times), nt, dptr(off), dptr(positions),
-            dptr(velocities) if velocities is not None else None, int(outputMode), float(reference_jd), int(layout)))
+            dptr(velocities) if velocities is not None else None, int(outputMode), float(reference_jd), int(layout),
+            mask.ctypes.data_as(C.c_void_p) if mask is not None else None, rows))
         return positions, velocities
-
 
     def screen_conjunction(self, times, target: int, threshold: float = 10.0, epoch_offsets=None,
                            reference_jd: float = 0.0):

@@ -86,6 +86,7 @@ struct Constellation {
     bool timePending = false;          // kept for call sites: set after recording timeCopied
     // stateless-path epoch offsets
     DevBuf<double> dToffCall;
+    DevBuf<uint8_t> dMask;
     double *hToffCall = nullptr;
     size_t hToffCap = 0;
     cudaEvent_t toffCopied = nullptr;
@@ -108,7 +109,7 @@ struct Constellation {
     ~Constellation() {
         cudaSetDevice(device);
         dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release();
-        dSdp4.release(); dTime.release(); dToffCall.release(); dLattice.release(); dPos.release(); dVel.release();
+        dSdp4.release(); dTime.release(); dToffCall.release(); dMask.release(); dLattice.release(); dPos.release(); dVel.release();
         dHead.release(); dNext.release(); dPairs.release(); dTIdx.release(); dCount.release();
         for (auto &h : hTimeSlot) if (h) cudaFreeHost(h);
         if (hToffCall) cudaFreeHost(hToffCall);
@@ -663,7 +664,7 @@ int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float
 // ---- stateless near-earth path -----------------------------------------------------------------
 static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t nt, const double *epoch_offsets,
                                 double *dPos, double *dVel, int mode, double reference_jd, int layout, cudaStream_t s,
-                                uint32_t recStride = 3) {
+                                uint32_t recStride = 3, const uint8_t *mask = nullptr, uint32_t outNumSats = 0) {
     const uint32_t ns = c->cat.nSgp4;
     const uint32_t padded = c->cat.sgp4Padded();
     int32_t rc = reserve_time(c, nt);
@@ -713,8 +714,13 @@ static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t 
     a.nTimes = nt;
     a.pos = dPos;
     a.vel = dVel;
-    a.outNumSats = ns;
+    a.outNumSats = outNumSats ? outNumSats : ns;
     a.recStride = recStride;
+    if (mask) {  // pageable host bytes: the copy is staged by the driver before the call returns
+        AZ_CUDA(c->dMask.reserve(ns));
+        AZ_CUDA(cudaMemcpyAsync(c->dMask.p, mask, ns, cudaMemcpyHostToDevice, s));
+        a.mask = c->dMask.p;
+    }
     AZ_CUDA(cudaEventRecord(c->ev[0], s));
     AZ_CUDA(az::launch_sgp4_grid(a, mode, layout, s, c->variant));
     AZ_CUDA(cudaEventRecord(c->ev[1], s));
@@ -726,30 +732,47 @@ static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t 
 
 int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const double *times, uint32_t n_times,
                                                const double *epoch_offsets, double *d_pos, double *d_vel, int32_t mode,
-                                               double reference_jd, int32_t layout, void *stream) {
+                                               double reference_jd, int32_t layout, const uint8_t *satellite_mask,
+                                               uint32_t out_num_sats, void *stream) {
     Constellation *c = static_cast<Constellation *>(h);
     int32_t rc = check_args(c, times, epoch_offsets, d_pos, mode, layout);
     if (rc != ASTROZ_OK) return rc;
     if (n_times == 0 || c->cat.nSgp4 == 0) return ASTROZ_OK;
+    if (out_num_sats && out_num_sats < c->cat.nSgp4) {
+        g_lastError = "out_num_sats smaller than the number of near-earth satellites";
+        return ASTROZ_VALUE_ERROR;
+    }
     AZ_CUDA(cudaSetDevice(c->device));
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
-    return sgp4_into_common(c, times, n_times, epoch_offsets, d_pos, d_vel, mode, reference_jd, layout, s);
+    return sgp4_into_common(c, times, n_times, epoch_offsets, d_pos, d_vel, mode, reference_jd, layout, s, 3,
+                            satellite_mask, out_num_sats);
 }
 
 int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *times, uint32_t n_times,
                                         const double *epoch_offsets, double *pos, double *vel, int32_t mode,
-                                        double reference_jd, int32_t layout) {
+                                        double reference_jd, int32_t layout, const uint8_t *satellite_mask,
+                                        uint32_t out_num_sats) {
     Constellation *c = static_cast<Constellation *>(h);
     int32_t rc = check_args(c, times, epoch_offsets, pos, mode, layout);
     if (rc != ASTROZ_OK) return rc;
     const uint32_t ns = c->cat.nSgp4;
     if (n_times == 0 || ns == 0) return ASTROZ_OK;
+    const uint32_t rows = out_num_sats ? out_num_sats : ns;
+    if (rows < ns) {
+        g_lastError = "out_num_sats smaller than the number of near-earth satellites";
+        return ASTROZ_VALUE_ERROR;
+    }
     AZ_CUDA(cudaSetDevice(c->device));
-    const size_t total = (size_t)ns * n_times * 3;
+    const size_t total = (size_t)rows * n_times * 3;
     AZ_CUDA(c->dPos.reserve(total));
     if (vel) AZ_CUDA(c->dVel.reserve(total));
+    const bool partial = satellite_mask != nullptr || rows != ns;
+    if (partial) {  // rows the kernel will not touch must keep the caller's contents
+        AZ_CUDA(cudaMemcpyAsync(c->dPos.p, pos, total * 8, cudaMemcpyHostToDevice, c->stream));
+        if (vel) AZ_CUDA(cudaMemcpyAsync(c->dVel.p, vel, total * 8, cudaMemcpyHostToDevice, c->stream));
+    }
     rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode, reference_jd,
-                          layout, c->stream);
+                          layout, c->stream, 3, satellite_mask, rows);
     if (rc != ASTROZ_OK) return rc;
     AZ_CUDA(cudaMemcpyAsync(pos, c->dPos.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
     if (vel) AZ_CUDA(cudaMemcpyAsync(vel, c->dVel.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -960,7 +983,7 @@ int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, d
             return ASTROZ_OK;
         }
         rc = astroz_cuda_sgp4_propagate_into(c, times, count, &zero, pos.data(), vel.data(), ASTROZ_MODE_TEME, 0.0,
-                                             ASTROZ_LAYOUT_SATELLITE_MAJOR);
+                                             ASTROZ_LAYOUT_SATELLITE_MAJOR, nullptr, 0);
         if (rc != ASTROZ_OK) return rc;
     } else {
         // deep space: minutes since epoch go to the kernel directly (no Julian-date round trip)

@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
         const uint32_t sat0 = tileIdx * kTileSats;
         const uint32_t row0 = __ldg(a.orig + sat0);
         const uint32_t nReal = min((uint32_t)kTileSats, a.nSats - sat0);
-        bool block8 = nReal == kTileSats && ((((size_t)a.outNumSats * 3) & 1) == 0) &&
+        bool block8 = nReal == kTileSats && a.mask == nullptr && ((((size_t)a.outNumSats * 3) & 1) == 0) &&
                       ((reinterpret_cast<uintptr_t>(a.pos + (size_t)row0 * 3) & 15u) == 0) &&
                       (!kVel || (reinterpret_cast<uintptr_t>(a.vel + (size_t)row0 * 3) & 15u) == 0);
 #pragma unroll
@@ -205,6 +205,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
                 auto col = [colBase](int i) { return colBase[i * kTileSats]; };
                 const double toff = __ldg(a.toff + sat);
                 const uint32_t row = __ldg(a.orig + sat);
+                if (a.mask && a.mask[row] == 0) continue;  // laneActive, src/Constellation.zig:530-533 (block8 is off with a mask)
                 double ts[kLanes];
 #pragma unroll
                 for (int k = 0; k < kLanes; ++k) ts[k] = __ldg(a.tbase + min(tw + 32u * k + lane, t1 - 1)) + toff;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
         auto col = [colBase](int i) { return colBase[i * kTileSats]; };
         const double toff = __ldg(a.toff + sat);
         const uint32_t row = __ldg(a.orig + sat);
+        if (a.mask && a.mask[row] == 0) continue;  // laneActive, src/Constellation.zig:530-533
         // a thread owns kLanes epochs of this satellite, 32 apart, so each warp-run is 32 consecutive epochs
         // (one contiguous 768-byte run of the satellite-major block).  The loop is warp-uniform.
 #pragma unroll 1

@@ -16,6 +16,7 @@ struct GridArgs {
     const double2 *lattice = nullptr;    // K2: [nSats][2][latticeNodes] (xli, xni) at atime = +-720*k
     int latticeNodes = 0;
     const uint32_t *orig = nullptr;      // output row of each table satellite (padded for K1)
+    const uint8_t *mask = nullptr;       // nullable: per output row, 0 = leave that satellite's rows untouched
     uint32_t nSats = 0;                  // real satellites in the table
     // time axis
     const double *tbase = nullptr;       // K1: minutes of each epoch relative to the reference epoch

@@ -139,17 +139,23 @@ int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, con
 int32_t astroz_cuda_constellation_reset_carry(astroz_constellation_t h);
 
 /* stateless near-earth path: replaces Constellation.propagateConstellation (src/Constellation.zig:541-605)
- * as called by SatrecArray.propagate_into (bindings/python/src/satrec.zig:896-988):
+ * as called by SatrecArray.propagate_into / Sgp4Constellation.propagate_into
+ * (bindings/python/src/satrec.zig:896-988, bindings/python/src/sgp4.zig:171-268):
  *   tsince[sat][t] = times[t] + epoch_offsets[sat]   (minutes)
- * Only the SGP4 satellites of `h` take part, in catalog order; n_sgp4 rows are written.
- * epoch_offsets: n_sgp4 doubles.  reference_jd is used for GMST when mode != TEME.  HOST buffers. */
+ * Only the SGP4 satellites of `h` take part, in catalog order: satellite i -> output row i.
+ * epoch_offsets: n_sgp4 doubles.  reference_jd is used for GMST when mode != TEME.
+ * satellite_mask (nullable, n_sgp4 bytes): rows whose byte is 0 are not computed and not written
+ * (src/Constellation.zig:436-446,530-533).  out_num_sats (0 = n_sgp4): row count of the output block, the
+ * reference's output_stride (bindings/python/src/sgp4.zig:215-216).  HOST buffers of out_num_sats*n_times*3. */
 int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *times, uint32_t n_times,
                                         const double *epoch_offsets, double *pos, double *vel, int32_t mode,
-                                        double reference_jd, int32_t layout);
-/* device-resident variant of the above (d_pos/d_vel device pointers) */
+                                        double reference_jd, int32_t layout, const uint8_t *satellite_mask,
+                                        uint32_t out_num_sats);
+/* device-resident variant of the above (d_pos/d_vel device pointers; the mask is still a HOST array) */
 int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const double *times, uint32_t n_times,
                                                const double *epoch_offsets, double *d_pos, double *d_vel,
-                                               int32_t mode, double reference_jd, int32_t layout, void *stream);
+                                               int32_t mode, double reference_jd, int32_t layout,
+                                               const uint8_t *satellite_mask, uint32_t out_num_sats, void *stream);
 
 /* Fused propagate + single-target conjunction screen: replaces Constellation.screenConstellation
  * (src/Constellation.zig:683-756) as called by Sgp4Constellation.screen_conjunction

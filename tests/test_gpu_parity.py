@@ -519,3 +519,29 @@ def test_odd_offsets_and_strides_take_the_unaligned_paths(az, synth):
             v = vel.cpu().numpy() if layout == 0 else vel.cpu().numpy().transpose(1, 0, 2)
             assert np.array_equal(p[3:44], ref_p) and np.array_equal(v[3:44], ref_v)
             assert np.all(p[:3] == -1.0) and np.all(p[44:] == -1.0)     # neighbours untouched
+
+
+def test_propagate_into_mask_and_output_stride(az, oracle, synth):
+    """satellite_mask and output_stride of Sgp4Constellation.propagate_into (bindings/python/src/sgp4.zig:171-268,
+    src/Constellation.zig:436-446,530-533): masked rows are left untouched, the block may be wider than the
+    constellation."""
+    tles = synth.near_earth_catalog(37)
+    c = az.Constellation(tles)
+    times = np.arange(0.0, 130.0, 2.0)
+    off = (2460437.5 - c.epochs) * 1440.0
+    full_p, full_v = c.propagate_into(times, epoch_offsets=off, time_major=False)
+    mask = np.ones(37, dtype=np.uint8)
+    mask[[0, 5, 8, 9, 36]] = 0
+    for tm in (False, True):
+        rows = 45
+        shape = (rows, len(times), 3) if not tm else (len(times), rows, 3)
+        p = np.full(shape, 7.0)
+        v = np.full(shape, 7.0)
+        c.propagate_into(times, p, v, epoch_offsets=off, satellite_mask=mask, time_major=tm, output_stride=rows)
+        ps = p if not tm else p.transpose(1, 0, 2)
+        vs = v if not tm else v.transpose(1, 0, 2)
+        on = np.flatnonzero(mask)
+        assert np.array_equal(ps[on], full_p[on]) and np.array_equal(vs[on], full_v[on])
+        assert np.all(ps[np.flatnonzero(mask == 0)] == 7.0) and np.all(ps[37:] == 7.0)
+    with pytest.raises(ValueError):
+        c.propagate_into(times, satellite_mask=np.ones(5, dtype=np.uint8))
