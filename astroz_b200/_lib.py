@@ -61,6 +61,8 @@ def lib() -> C.CDLL:
         "astroz_cuda_constellation_create_from_text": (i32, [C.c_char_p, C.c_size_t, i32, i32, C.POINTER(vp)]),
         "astroz_cuda_constellation_create_from_elements": (i32, [dp, dp, dp, dp, dp, dp, dp, dp, u32, i32, i32,
                                                                  C.POINTER(vp)]),
+        "astroz_cuda_constellation_create_from_elements_device": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, u32, i32, i32,
+                                                                        C.POINTER(vp)]),
         "astroz_cuda_constellation_free": (None, [vp]),
         "astroz_cuda_constellation_counts": (i32, [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]),
         "astroz_cuda_constellation_epochs": (i32, [vp, dp]),
@@ -102,7 +104,8 @@ def lib() -> C.CDLL:
 EXPORTS = [
     "astroz_cuda_version", "astroz_cuda_device_count", "astroz_cuda_last_error", "astroz_cuda_host_alloc",
     "astroz_cuda_host_free", "astroz_cuda_constellation_create", "astroz_cuda_constellation_create_from_text",
-    "astroz_cuda_constellation_create_from_elements", "astroz_cuda_constellation_free",
+    "astroz_cuda_constellation_create_from_elements", "astroz_cuda_constellation_create_from_elements_device",
+    "astroz_cuda_constellation_free",
     "astroz_cuda_constellation_counts", "astroz_cuda_constellation_epochs",
     "astroz_cuda_constellation_classes", "astroz_cuda_constellation_get_reference_epoch",
     "astroz_cuda_constellation_set_reference_epoch", "astroz_cuda_constellation_propagate",

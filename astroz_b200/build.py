@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libastroz_b200.so")
-SOURCES = ["az_kernels.cu", "az_capi.cu"]
-HEADERS = ["az_math.cuh", "az_device.cuh", "az_kernels.cuh", "az_elements.hpp", "az_tables.hpp",
+SOURCES = ["az_kernels.cu", "az_ingest.cu", "az_capi.cu"]
+HEADERS = ["az_math.cuh", "az_device.cuh", "az_kernels.cuh", "az_ingest.cuh", "az_elements.hpp", "az_tables.hpp",
            os.path.join("..", "..", "include", "astroz_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

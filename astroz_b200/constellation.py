@@ -92,6 +92,33 @@ class Constellation:
         self.device, self.grav = int(device), int(grav)
         return self
 
+    @classmethod
+    def from_device_elements(cls, elements, grav: int = _lib.WGS72) -> "Constellation":
+        """Build from element columns that already live in HBM: `elements` is a CUDA float64 tensor of shape (8, n)
+        whose rows are epoch_jd, mean_motion_rev_day, ecc, incl_deg, raan_deg, argp_deg, ma_deg, bstar (the order of
+        `from_elements`).  Classification, Sgp4/Sdp4.initElements (src/Sgp4.zig:108-417, src/Sdp4.zig:174-657) and
+        the table build (src/Constellation.zig:101-200) run on the device (K5); the element values never visit the
+        host.  Results match `from_elements` to the last few ulps of the device's libm."""
+        import torch
+        if not (isinstance(elements, torch.Tensor) and elements.is_cuda and elements.dtype == torch.float64 and
+                elements.dim() == 2 and elements.shape[0] == 8):
+            raise ValueError("elements must be a CUDA float64 tensor of shape (8, n)")
+        elements = elements.contiguous()
+        n = int(elements.shape[1])
+        device = elements.device.index or 0
+        torch.cuda.current_stream(device).synchronize()  # the library reads the columns on its own stream
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        self._free = lib().astroz_cuda_constellation_free
+        ptrs = [C.c_void_p(elements[k].data_ptr()) for k in range(8)]
+        check(lib().astroz_cuda_constellation_create_from_elements_device(*ptrs, n, int(grav), int(device),
+                                                                           C.byref(self._h)))
+        cn, ns, nd = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        check(lib().astroz_cuda_constellation_counts(self._h, C.byref(cn), C.byref(ns), C.byref(nd)))
+        self.numSatellites, self.numSgp4, self.numSdp4 = cn.value, ns.value, nd.value
+        self.device, self.grav = int(device), int(grav)
+        return self
+
     def deinit(self) -> None:
         """Constellation.deinit (src/Constellation.zig:202-210)."""
         if getattr(self, "_h", None) is not None and self._h:

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "az_ingest.cuh"
 #include "az_kernels.cuh"
 #include "az_tables.hpp"
 
@@ -66,6 +67,7 @@ struct Constellation {
     int device = 0;
     az::CatalogTables cat;
     az::GravConsts g{};
+    double sdp4EpochMin = INFINITY, sdp4EpochMax = -INFINITY;  // epoch span of the deep-space records
     cudaStream_t stream = nullptr, copyStream = nullptr;
     // element tables (resident for the life of the handle)
     DevBuf<double> dTiles, dToff;
@@ -132,7 +134,7 @@ int32_t upload_toff(Constellation *c) {  // src/Constellation.zig:153
     return ASTROZ_OK;
 }
 
-int32_t finish_create(Constellation *c, int device) {
+int32_t open_device(Constellation *c, int device) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
     if (e != cudaSuccess || count == 0) {
@@ -152,6 +154,15 @@ int32_t finish_create(Constellation *c, int device) {
     c->timeCopied = c->slotCopied[0];
     for (auto &ev : c->ev) AZ_CUDA(cudaEventCreate(&ev));
     for (auto &ev : c->chunkDone) AZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    if (const char *v = std::getenv("ASTROZ_SGP4_VARIANT")) c->variant = std::atoi(v);
+    if (const char *v = std::getenv("ASTROZ_SDP4_VARIANT")) az::set_sdp4_variant(std::atoi(v));
+    if (const char *v = std::getenv("ASTROZ_D2H_CHUNKS")) c->chunks = std::max(1, std::min(64, std::atoi(v)));
+    return ASTROZ_OK;
+}
+
+int32_t finish_create(Constellation *c, int device) {
+    int32_t rc0 = open_device(c, device);
+    if (rc0 != ASTROZ_OK) return rc0;
     c->g = az::grav_consts(c->cat.grav);
     const az::CatalogTables &t = c->cat;
     if (t.nSgp4) {
@@ -171,11 +182,95 @@ int32_t finish_create(Constellation *c, int device) {
         AZ_CUDA(cudaMemcpy(c->dSdp4.p, t.sdp4.data(), t.nSdp4 * sizeof(az::Sdp4Sat), cudaMemcpyHostToDevice));
         AZ_CUDA(c->dSdp4Orig.reserve(t.nSdp4));
         AZ_CUDA(cudaMemcpy(c->dSdp4Orig.p, t.sdp4Orig.data(), t.nSdp4 * 4, cudaMemcpyHostToDevice));
+        for (const az::Sdp4Sat &r : t.sdp4) {
+            c->sdp4EpochMin = std::min(c->sdp4EpochMin, r.epochJd);
+            c->sdp4EpochMax = std::max(c->sdp4EpochMax, r.epochJd);
+        }
     }
-    if (const char *v = std::getenv("ASTROZ_SGP4_VARIANT")) c->variant = std::atoi(v);
-    if (const char *v = std::getenv("ASTROZ_SDP4_VARIANT")) az::set_sdp4_variant(std::atoi(v));
-    if (const char *v = std::getenv("ASTROZ_D2H_CHUNKS")) c->chunks = std::max(1, std::min(64, std::atoi(v)));
     return ASTROZ_OK;
+}
+
+// Device-side ingest (K5, az_ingest.cu): the element columns are already in HBM; classification, initialisation and
+// the table scatter run there.  The host keeps only what later calls need: counts, epochs, classes, row maps.
+int32_t ingest_on_device(Constellation *c, az::IngestArgs a, int grav) {
+    cudaStream_t s = c->stream;
+    az::CatalogTables &t = c->cat;
+    t = az::CatalogTables{};
+    t.n = a.n;
+    t.grav = az::gravity(grav);
+    a.grav = t.grav;
+    c->g = az::grav_consts(t.grav);
+    if (a.n == 0) return ASTROZ_OK;
+    const uint32_t blocks = az::ingest_block_count(a.n);
+    DevBuf<uint8_t> flags;
+    DevBuf<uint32_t> counts;   // blockNear | blockDeep | totals[2]
+    DevBuf<unsigned long long> fail;
+    DevBuf<int32_t> classes;
+    struct Release {
+        DevBuf<uint8_t> &a; DevBuf<uint32_t> &b; DevBuf<unsigned long long> &c; DevBuf<int32_t> &d;
+        ~Release() { a.release(); b.release(); c.release(); d.release(); }
+    } release{flags, counts, fail, classes};
+    AZ_CUDA(flags.reserve(a.n));
+    AZ_CUDA(counts.reserve((size_t)blocks * 2 + 2));
+    AZ_CUDA(fail.reserve(1));
+    AZ_CUDA(classes.reserve(a.n));
+    a.flags = flags.p;
+    a.blockNear = counts.p;
+    a.blockDeep = counts.p + blocks;
+    a.totals = counts.p + 2 * (size_t)blocks;
+    a.firstFail = fail.p;
+    a.classes = classes.p;
+    AZ_CUDA(cudaMemsetAsync(fail.p, 0xff, 8, s));
+    AZ_CUDA(az::launch_ingest_classify(a, s));
+    uint32_t totals[2] = {0, 0};
+    unsigned long long firstFail = ~0ull;
+    AZ_CUDA(cudaMemcpyAsync(totals, a.totals, 8, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(&firstFail, fail.p, 8, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    if (firstFail != ~0ull) {
+        g_lastError = "element set " + std::to_string(firstFail >> 8) + " failed to initialise";
+        return status_to_code((int)(firstFail & 0xff));
+    }
+    t.nSgp4 = totals[0];
+    t.nSdp4 = totals[1];
+    const uint32_t padded = t.sgp4Padded();
+    if (t.nSgp4) {
+        AZ_CUDA(c->dTiles.reserve((size_t)t.sgp4Tiles_count() * az::kSgp4TileDoubles));
+        AZ_CUDA(c->dSgp4Orig.reserve(padded));
+        AZ_CUDA(c->dIdentity.reserve(padded));
+    }
+    if (t.nSdp4) {
+        AZ_CUDA(c->dSdp4.reserve(t.nSdp4));
+        AZ_CUDA(c->dSdp4Orig.reserve(t.nSdp4));
+    }
+    a.tiles = c->dTiles.p;
+    a.sgp4Orig = c->dSgp4Orig.p;
+    a.identity = c->dIdentity.p;
+    a.sdp4 = c->dSdp4.p;
+    a.sdp4Orig = c->dSdp4Orig.p;
+    AZ_CUDA(az::launch_ingest_build(a, s));
+    t.epochs.resize(a.n);
+    t.classes.resize(a.n);
+    t.sgp4Orig.resize(padded);
+    t.sdp4Orig.resize(t.nSdp4);
+    AZ_CUDA(cudaMemcpyAsync(t.epochs.data(), a.epochJd, (size_t)a.n * 8, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(t.classes.data(), classes.p, (size_t)a.n * 4, cudaMemcpyDeviceToHost, s));
+    if (padded) AZ_CUDA(cudaMemcpyAsync(t.sgp4Orig.data(), c->dSgp4Orig.p, (size_t)padded * 4, cudaMemcpyDeviceToHost, s));
+    if (t.nSdp4) AZ_CUDA(cudaMemcpyAsync(t.sdp4Orig.data(), c->dSdp4Orig.p, (size_t)t.nSdp4 * 4, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaMemcpyAsync(&firstFail, fail.p, 8, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
+    if (firstFail != ~0ull) {
+        g_lastError = "element set " + std::to_string(firstFail >> 8) + " failed to initialise";
+        return status_to_code((int)(firstFail & 0xff));
+    }
+    t.sgp4Epoch.resize(padded);
+    for (uint32_t i = 0; i < padded; ++i) t.sgp4Epoch[i] = t.epochs[t.sgp4Orig[i]];
+    if (t.nSgp4) t.referenceEpochJd = t.sgp4Epoch[0];  // src/Constellation.zig:139-140
+    for (uint32_t i = 0; i < t.nSdp4; ++i) {
+        c->sdp4EpochMin = std::min(c->sdp4EpochMin, t.epochs[t.sdp4Orig[i]]);
+        c->sdp4EpochMax = std::max(c->sdp4EpochMax, t.epochs[t.sdp4Orig[i]]);
+    }
+    return upload_toff(c);
 }
 
 // host staging for the time axis; waits for the previous call's async upload before reuse
@@ -319,11 +414,7 @@ int32_t upload_time_axis(Constellation *c, const double *jd, const double *fr, u
 
 int32_t prepare_deep_space(Constellation *c, double jdMin, double jdMax, cudaStream_t s) {
     if (c->cat.nSdp4 == 0) return ASTROZ_OK;
-    double eMin = INFINITY, eMax = -INFINITY;
-    for (const az::Sdp4Sat &r : c->cat.sdp4) {
-        eMin = std::min(eMin, r.epochJd);
-        eMax = std::max(eMax, r.epochJd);
-    }
+    const double eMin = c->sdp4EpochMin, eMax = c->sdp4EpochMax;
     const double reach = std::max(std::fabs((jdMax - eMin) * 1440.0), std::fabs((jdMin - eMax) * 1440.0));
     return ensure_lattice(c, (int)std::floor(reach / az::kStepp) + 2, s);
 }
@@ -430,6 +521,38 @@ int32_t astroz_cuda_constellation_create_from_elements(const double *epoch_jd, c
         return status_to_code(rc);
     }
     int32_t e = finish_create(c, device);
+    if (e != ASTROZ_OK) {
+        delete c;
+        return e;
+    }
+    *out = c;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_create_from_elements_device(
+    const double *d_epoch_jd, const double *d_mean_motion_rev_day, const double *d_ecc, const double *d_incl_deg,
+    const double *d_raan_deg, const double *d_argp_deg, const double *d_ma_deg, const double *d_bstar, uint32_t n,
+    int32_t grav, int32_t device, astroz_constellation_t *out) {
+    if (!out || (n && (!d_epoch_jd || !d_mean_motion_rev_day || !d_ecc || !d_incl_deg || !d_raan_deg || !d_argp_deg ||
+                       !d_ma_deg || !d_bstar)))
+        return ASTROZ_NULL_POINTER;
+    *out = nullptr;
+    Constellation *c = new (std::nothrow) Constellation();
+    if (!c) return ASTROZ_ALLOC_FAILED;
+    int32_t e = open_device(c, device);
+    if (e == ASTROZ_OK) {
+        az::IngestArgs a;
+        a.epochJd = d_epoch_jd;
+        a.revPerDay = d_mean_motion_rev_day;
+        a.ecc = d_ecc;
+        a.inclDeg = d_incl_deg;
+        a.raanDeg = d_raan_deg;
+        a.argpDeg = d_argp_deg;
+        a.maDeg = d_ma_deg;
+        a.bstar = d_bstar;
+        a.n = n;
+        e = ingest_on_device(c, a, grav);
+    }
     if (e != ASTROZ_OK) {
         delete c;
         return e;

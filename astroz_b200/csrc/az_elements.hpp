@@ -12,6 +12,14 @@
 #include <cstring>
 #include <string>
 
+// The element builders below are plain arithmetic over <cmath>; under nvcc they are also compiled for the
+// device, where the ingest kernels (az_ingest.cu) run them one satellite per thread.
+#ifdef __CUDACC__
+#define AZ_EHD __host__ __device__
+#else
+#define AZ_EHD
+#endif
+
 namespace az {
 
 // kernel-level status codes (src/simdKernels.zig:30-37)
@@ -21,7 +29,7 @@ struct Gravity {  // src/constants.zig:30-64
     double radiusEarthKm, mu, j2, j3, j4, xke, tumin, j3oj2;
 };
 
-inline Gravity gravity(int which) {
+AZ_EHD inline Gravity gravity(int which) {
     if (which == 1) return {6378.135, 398600.8, 0.001082616, -0.00000253881, -0.00000165597, 0.0743669161331734132,
                             13.44683969695931, -0.00234506972242078};
     return {6378.137, 398600.5, 0.00108262998905, -0.00000253215306, -0.00000161098761, 0.07436685316871385,
@@ -38,7 +46,7 @@ constexpr double kHPi = 3.14159265358979323846264338327950288;
 constexpr double kHTwoPi = 2.0 * kHPi;
 constexpr double kDeg = kHPi / 180.0;
 
-inline double wrap(double x, double m) {  // Zig @mod: sign of the divisor
+AZ_EHD inline double wrap(double x, double m) {  // Zig @mod: sign of the divisor
     double r = std::fmod(x, m);
     if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
     return r;
@@ -134,7 +142,7 @@ struct NearEarth {
 
 // Steps shared by SGP4 and SDP4 init (src/Sgp4.zig:192-382).  Returns kOk / kInvalidEcc / kDecayed,
 // and reports the orbital period so the caller can classify (src/Sgp4.zig:120-123).
-inline int build_common(const TleRecord &t, const Gravity &g, NearEarth &o, double &periodMin, double &perigeeKm) {
+AZ_EHD inline int build_common(const TleRecord &t, const Gravity &g, NearEarth &o, double &periodMin, double &perigeeKm) {
     using namespace detail;
     o = NearEarth{};
     o.epochJd = t.epochJd;
@@ -226,7 +234,7 @@ inline int build_common(const TleRecord &t, const Gravity &g, NearEarth &o, doub
 }
 
 // src/Sgp4.zig:108-180: kOk, kInvalidEcc, kDecayed or kDeepSpace (period > 225 min)
-inline int build_near_earth(const TleRecord &t, const Gravity &g, NearEarth &o) {
+AZ_EHD inline int build_near_earth(const TleRecord &t, const Gravity &g, NearEarth &o) {
     double period = 0, perigee = 0;
     int rc = build_common(t, g, o, period, perigee);
     if (rc != kOk) return rc;
@@ -262,7 +270,7 @@ struct DeepSpace {
     double xlamo, xfact, gsto;
 };
 
-inline double gstime(double jdut1) {  // src/Sdp4.zig:277-285
+AZ_EHD inline double gstime(double jdut1) {  // src/Sdp4.zig:277-285
     const double tu = (jdut1 - 2451545.0) / 36525.0;
     double sec = -6.2e-6 * tu * tu * tu + 0.093104 * tu * tu + (876600.0 * 3600.0 + 8640184.812866) * tu + 67310.54841;
     double th = detail::wrap(sec * detail::kDeg / 240.0, detail::kHTwoPi);
@@ -276,7 +284,7 @@ struct ThirdBody {  // one pass of the dscom loop (src/Sdp4.zig:391-436)
     double z1, z2, z3, z11, z12, z13, z21, z22, z23, z31, z32, z33;
 };
 
-inline ThirdBody third_body(double zcosg, double zsing, double zcosi, double zsini, double zcosh, double zsinh,
+AZ_EHD inline ThirdBody third_body(double zcosg, double zsing, double zcosi, double zsini, double zcosh, double zsinh,
                             double cc, double sinim, double cosim, double sinomm, double cosomm, double emsq,
                             double ecco, double rtemsq, double xnoi) {
     const double a1 = zcosg * zcosh + zsing * zcosi * zsinh;
@@ -324,7 +332,7 @@ inline ThirdBody third_body(double zcosg, double zsing, double zcosi, double zsi
     return b;
 }
 
-inline LuniSolar periodic_coeffs(const ThirdBody &b, double emsq, double ze) {  // src/Sdp4.zig:69-105
+AZ_EHD inline LuniSolar periodic_coeffs(const ThirdBody &b, double emsq, double ze) {  // src/Sdp4.zig:69-105
     LuniSolar p;
     p.e2 = 2.0 * b.s1 * b.s6;
     p.e3 = 2.0 * b.s1 * b.s7;
@@ -341,18 +349,21 @@ inline LuniSolar periodic_coeffs(const ThirdBody &b, double emsq, double ze) {  
     return p;
 }
 
-inline double horner_up(double x, std::initializer_list<double> c) {  // src/Sdp4.zig:671-679 (ascending powers)
-    double acc = 0.0, xn = 1.0;
-    for (double ci : c) {
-        acc += ci * xn;
-        xn *= x;
-    }
+AZ_EHD inline double horner_up(double x, double c0, double c1, double c2, double c3 = 0.0) {
+    // src/Sdp4.zig:671-679: ascending powers, term by term (a cubic, or a quadratic with c3 = 0)
+    double acc = c0;
+    double xn = x;
+    acc += c1 * xn;
+    xn *= x;
+    acc += c2 * xn;
+    xn *= x;
+    acc += c3 * xn;
     return acc;
 }
 }  // namespace detail
 
 // src/Sdp4.zig:174-274 (initElements), :344-499 (dscom), :525-657 (dsinit)
-inline int build_deep_space(const TleRecord &t, const Gravity &g, DeepSpace &d) {
+AZ_EHD inline int build_deep_space(const TleRecord &t, const Gravity &g, DeepSpace &d) {
     using namespace detail;
     constexpr double zes = 0.01675, zel = 0.05490, c1ss = 2.9864797e-6, c1l = 4.7968065e-7;
     constexpr double zsinis = 0.39785416, zcosis = 0.91744867, zcosgs = 0.1945905, zsings = -0.98088458;
@@ -451,18 +462,18 @@ inline int build_deep_space(const TleRecord &t, const Gravity &g, DeepSpace &d) 
         const double ec = e.ecco;
         const bool lo65 = ec <= 0.65, lo70 = ec < 0.7;
         const double g201 = -0.306 - (ec - 0.64) * 0.440;
-        const double g211 = lo65 ? horner_up(ec, {3.616, -13.2470, 16.2900}) : horner_up(ec, {-72.099, 331.819, -508.738, 266.724});
-        const double g310 = lo65 ? horner_up(ec, {-19.302, 117.3900, -228.4190, 156.591}) : horner_up(ec, {-346.844, 1582.851, -2415.925, 1246.113});
-        const double g322 = lo65 ? horner_up(ec, {-18.9068, 109.7927, -214.6334, 146.5816}) : horner_up(ec, {-342.585, 1554.908, -2366.899, 1215.972});
-        const double g410 = lo65 ? horner_up(ec, {-41.122, 242.6940, -471.0940, 313.953}) : horner_up(ec, {-1052.797, 4758.686, -7193.992, 3651.957});
-        const double g422 = lo65 ? horner_up(ec, {-146.407, 841.8800, -1629.014, 1083.435}) : horner_up(ec, {-3581.690, 16178.110, -24462.770, 12422.520});
+        const double g211 = lo65 ? horner_up(ec, 3.616, -13.2470, 16.2900) : horner_up(ec, -72.099, 331.819, -508.738, 266.724);
+        const double g310 = lo65 ? horner_up(ec, -19.302, 117.3900, -228.4190, 156.591) : horner_up(ec, -346.844, 1582.851, -2415.925, 1246.113);
+        const double g322 = lo65 ? horner_up(ec, -18.9068, 109.7927, -214.6334, 146.5816) : horner_up(ec, -342.585, 1554.908, -2366.899, 1215.972);
+        const double g410 = lo65 ? horner_up(ec, -41.122, 242.6940, -471.0940, 313.953) : horner_up(ec, -1052.797, 4758.686, -7193.992, 3651.957);
+        const double g422 = lo65 ? horner_up(ec, -146.407, 841.8800, -1629.014, 1083.435) : horner_up(ec, -3581.690, 16178.110, -24462.770, 12422.520);
         double g520;
-        if (lo65) g520 = horner_up(ec, {-532.114, 3017.977, -5740.032, 3708.276});
-        else if (ec > 0.715) g520 = horner_up(ec, {-5149.66, 29936.92, -54087.36, 31324.56});
+        if (lo65) g520 = horner_up(ec, -532.114, 3017.977, -5740.032, 3708.276);
+        else if (ec > 0.715) g520 = horner_up(ec, -5149.66, 29936.92, -54087.36, 31324.56);
         else g520 = 1464.74 - 4664.75 * ec + 3763.64 * ec * ec;
-        const double g521 = lo70 ? horner_up(ec, {-822.71072, 4568.6173, -8491.4146, 5337.524}) : horner_up(ec, {-51752.104, 218913.95, -309468.16, 146349.42});
-        const double g532 = lo70 ? horner_up(ec, {-853.66600, 4690.2500, -8624.7700, 5341.400}) : horner_up(ec, {-40023.880, 170470.89, -242699.48, 115605.82});
-        const double g533 = lo70 ? horner_up(ec, {-919.22770, 4988.6100, -9064.7700, 5542.21}) : horner_up(ec, {-37995.780, 161616.52, -229838.20, 109377.94});
+        const double g521 = lo70 ? horner_up(ec, -822.71072, 4568.6173, -8491.4146, 5337.524) : horner_up(ec, -51752.104, 218913.95, -309468.16, 146349.42);
+        const double g532 = lo70 ? horner_up(ec, -853.66600, 4690.2500, -8624.7700, 5341.400) : horner_up(ec, -40023.880, 170470.89, -242699.48, 115605.82);
+        const double g533 = lo70 ? horner_up(ec, -919.22770, 4988.6100, -9064.7700, 5542.21) : horner_up(ec, -37995.780, 161616.52, -229838.20, 109377.94);
         const double ci = e.cosio, si = e.sinio;
         const double f220 = 0.75 * (1.0 + 2.0 * ci + cosisq);
         const double f221 = 1.5 * sini2;
@@ -500,7 +511,7 @@ inline int build_deep_space(const TleRecord &t, const Gravity &g, DeepSpace &d) 
 }
 
 // GMST for the ECEF / geodetic output modes (src/WorldCoordinateSystem.zig:146-154)
-inline double julian_to_gmst(double jd) {
+AZ_EHD inline double julian_to_gmst(double jd) {
     const double d = jd - 2451545.0;
     const double t = d / 36525.0;
     double gmst = 280.46061837 + 360.98564736629 * d + 0.000387933 * t * t - t * t * t / 38710000.0;

@@ -16,12 +16,12 @@
 
 namespace az {
 
-inline GravConsts grav_consts(const Gravity &g) {
+AZ_EHD inline GravConsts grav_consts(const Gravity &g) {
     return GravConsts{g.j2, g.radiusEarthKm, g.xke * g.radiusEarthKm / 60.0, g.j3oj2, g.xke};
 }
 
 // column values of one near-earth satellite, in Sgp4Col order
-inline void sgp4_columns(const NearEarth &e, double *c) {
+AZ_EHD inline void sgp4_columns(const NearEarth &e, double *c) {
     c[kMo] = e.mo; c[kMdot] = e.mdot; c[kArgpo] = e.argpo; c[kArgpdot] = e.argpdot;
     c[kNodeo] = e.nodeo; c[kNodedot] = e.nodedot; c[kXnodcf] = e.xnodcf; c[kCc1] = e.cc1;
     c[kBc4] = e.bstar * e.cc4;  // only ever used as bstar*cc4 (src/Sgp4Batch.zig:126)
@@ -34,7 +34,7 @@ inline void sgp4_columns(const NearEarth &e, double *c) {
     c[kIsimp] = e.isimp ? 1.0 : 0.0;
 }
 
-inline Sdp4Sat sdp4_record(const DeepSpace &d) {
+AZ_EHD inline Sdp4Sat sdp4_record(const DeepSpace &d) {
     const NearEarth &e = d.ne;
     Sdp4Sat r{};
     r.mo = e.mo; r.mdot = e.mdot; r.argpo = e.argpo; r.argpdot = e.argpdot; r.nodeo = e.nodeo; r.nodedot = e.nodedot;

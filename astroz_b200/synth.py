@@ -166,3 +166,22 @@ def monte_carlo_catalog(n: int = 10000, seed: int = 12345, base: tuple[str, str]
             max(ecc + rng.normal(0, 1e-5), 1e-7), argp + rng.normal(0, 0.01), ma + rng.normal(0, 0.01),
             nn + rng.normal(0, 1e-5), bstar * (1.0 + rng.normal(0, 0.1))))
     return out
+
+
+def elements_from_tles(tles) -> np.ndarray:
+    """(8, n) float64 element columns in the order of `Constellation.from_elements` -- epoch_jd, mean_motion_rev_day,
+    ecc, incl_deg, raan_deg, argp_deg, ma_deg, bstar -- read from the fixed TLE columns (src/Tle.zig:49-101)."""
+    out = np.empty((8, len(tles)))
+    for i, (l1, l2) in enumerate(tles):
+        yy = int(l1[18:20])
+        year = 2000 + yy if yy < 57 else 1900 + yy
+        jan0 = 367.0 * year - math.floor(7 * (year + 0) / 4) + 30 + 1721013.5  # JD of <year> Jan 0.0 (1901..2099)
+        out[0, i] = jan0 + float(l1[20:32])
+        out[1, i] = float(l2[52:63])
+        out[2, i] = float(l2[26:33]) * 1e-7
+        out[3, i] = float(l2[8:16])
+        out[4, i] = float(l2[17:25])
+        out[5, i] = float(l2[34:42])
+        out[6, i] = float(l2[43:51])
+        out[7, i] = float(l1[53:59]) * 1e-5 * 10.0 ** int(l1[59:61])
+    return out

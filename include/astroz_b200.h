@@ -89,6 +89,15 @@ int32_t astroz_cuda_constellation_create_from_elements(const double *epoch_jd, c
                                                        uint32_t n, int32_t grav, int32_t device,
                                                        astroz_constellation_t *out);
 
+/* Same, with the eight element columns already resident in HBM on `device` (DEVICE pointers): classification,
+ * Sgp4.initElements / Sdp4.initElements (src/Sgp4.zig:108-417, src/Sdp4.zig:174-657) and the table build of
+ * src/Constellation.zig:101-200 run on the GPU, one element set per thread; nothing but counts, epochs and the row
+ * maps (16 B per set) returns to the host.  For Monte-Carlo draws and OMM streams generated on the device. */
+int32_t astroz_cuda_constellation_create_from_elements_device(
+    const double *d_epoch_jd, const double *d_mean_motion_rev_day, const double *d_ecc, const double *d_incl_deg,
+    const double *d_raan_deg, const double *d_argp_deg, const double *d_ma_deg, const double *d_bstar, uint32_t n,
+    int32_t grav, int32_t device, astroz_constellation_t *out);
+
 void astroz_cuda_constellation_free(astroz_constellation_t h);
 
 /* numSatellites / numSgp4 / numSdp4 (src/Constellation.zig:82,89,95) */

@@ -545,3 +545,57 @@ def test_propagate_into_mask_and_output_stride(az, oracle, synth):
         assert np.all(ps[np.flatnonzero(mask == 0)] == 7.0) and np.all(ps[37:] == 7.0)
     with pytest.raises(ValueError):
         c.propagate_into(times, satellite_mask=np.ones(5, dtype=np.uint8))
+
+
+def test_device_side_element_init_matches_host_init(az, synth):
+    """K5: element columns resident in HBM -> classification + Sgp4/Sdp4.initElements + table build on the
+    device (src/Constellation.zig:101-200, src/Sgp4.zig:108-417, src/Sdp4.zig:174-657).  Must reproduce the host
+    ingest: same classes, row maps and reference epoch, and the same trajectories to the device libm's last ulps."""
+    import torch
+    for n in (1, 7, 1000, 2051):
+        tles = synth.mixed_catalog(n, n_geo=max(1, n // 12), n_molniya=max(1, n // 40), n_gps=max(1, n // 40)) \
+            if n >= 7 else synth.near_earth_catalog(n)
+        el = synth.elements_from_tles(tles)
+        host = az.Constellation.from_elements(*el)
+        dev = az.Constellation.from_device_elements(torch.from_numpy(el).cuda())
+        assert (dev.numSatellites, dev.numSgp4, dev.numSdp4) == (host.numSatellites, host.numSgp4, host.numSdp4)
+        assert np.array_equal(dev.classes, host.classes) and np.array_equal(dev.epochs, host.epochs)
+        assert dev.referenceEpochJd == host.referenceEpochJd
+        if n >= 1000:
+            assert host.numSdp4 > 0 and len(set(host.classes.tolist())) == 4
+        jd = np.full(61, 2460437.5)
+        fr = np.linspace(0.0, 3.0, 61)
+        for layout in (az.Layout.satelliteMajor, az.Layout.timeMajor):
+            ph, vh = host.propagate(jd, fr, layout=layout)
+            pd, vd = dev.propagate(jd, fr, layout=layout)
+            assert np.max(np.abs(pd - ph)) < 1e-8 and np.max(np.abs(vd - vh)) < 1e-11
+
+
+def test_device_side_element_init_large_and_errors(az, synth):
+    import torch
+    # more than 1024 blocks of 256 element sets: the block-offset scan carries between its passes
+    n = 300_001
+    base = synth.elements_from_tles(synth.mixed_catalog(4096, n_geo=300, n_molniya=100, n_gps=100))
+    idx = np.random.default_rng(5).integers(0, base.shape[1], n)
+    el = np.ascontiguousarray(base[:, idx])
+    host = az.Constellation.from_elements(*el)
+    dev = az.Constellation.from_device_elements(torch.from_numpy(el).cuda())
+    assert (dev.numSgp4, dev.numSdp4) == (host.numSgp4, host.numSdp4)
+    assert np.array_equal(dev.classes, host.classes)
+    jd = np.full(3, 2460437.5)
+    fr = np.array([0.0, 0.4, 0.9])
+    ph, vh = host.propagate(jd, fr)
+    pd, vd = dev.propagate(jd, fr)
+    assert np.max(np.abs(pd - ph)) < 1e-8 and np.max(np.abs(vd - vh)) < 1e-11
+    # the first failing element set in catalog order decides the error (src/Constellation.zig:115-126)
+    bad = el[:, :5000].copy()
+    bad[2, 4100] = 1.5      # eccentricity >= 1  -> InvalidEccentricity
+    bad[1, 3000] = 17.9     # perigee below the surface -> SatelliteDecayed
+    with pytest.raises(az.AstrozCudaError) as eh:
+        az.Constellation.from_elements(*bad)
+    with pytest.raises(az.AstrozCudaError) as ed:
+        az.Constellation.from_device_elements(torch.from_numpy(bad).cuda())
+    assert ed.value.code == eh.value.code
+    assert b"element set 3000 " in az.lib().astroz_cuda_last_error()
+    empty = az.Constellation.from_device_elements(torch.empty((8, 0), dtype=torch.float64, device="cuda"))
+    assert empty.numSatellites == 0
