@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
         "astroz_cuda_sgp4_free": (None, [vp]),
         "astroz_cuda_sgp4_is_deep_space": (i32, [vp]),
         "astroz_cuda_sgp4_epoch": (i32, [vp, dp]),
+        "astroz_cuda_sgp4_elements": (i32, [vp, dp]),
         "astroz_cuda_sgp4_propagate": (i32, [vp, C.c_double, dp, dp]),
         "astroz_cuda_sgp4_propagate_batch": (i32, [vp, dp, dp, u32]),
         "astroz_cuda_sgp4_array": (i32, [vp, dp, dp, C.c_double, dp, u32]),
@@ -114,7 +115,7 @@ EXPORTS = [
     "astroz_cuda_constellation_synchronize", "astroz_cuda_constellation_last_kernel_ms",
     "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sgp4_screen",
     "astroz_cuda_constellation_coarse_screen_device", "astroz_cuda_sgp4_screen_all", "astroz_cuda_sgp4_init",
-    "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch",
+    "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch", "astroz_cuda_sgp4_elements",
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",
     "astroz_cuda_fp64_peak",
 ]

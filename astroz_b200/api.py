@@ -87,8 +87,27 @@ class Satrec:
         self.jdsatepoch = math.floor(ep.value - 0.5) + 0.5   # satrec.zig:124-126
         self.jdsatepochF = ep.value - self.jdsatepoch
         self.is_deep_space = bool(lib().astroz_cuda_sgp4_is_deep_space(self._h))
-        self.satnum = int(line1[2:7]) if line1[2:7].strip().isdigit() else 0
+        self._read_elements()
         return self
+
+    def _read_elements(self) -> None:
+        """python-sgp4 attribute set of the native Satrec (bindings/python/src/satrec.zig:385-494): TLE fields in
+        python-sgp4 units (radians, rad/min) and the un-Kozai'd semi-major axis with its apsis altitudes (earth radii)."""
+        l1 = self.line1
+        sn = l1[2:7].strip()
+        if sn[:1].isalpha():  # Alpha-5 catalog numbers, src/Tle.zig:281-290
+            self.satnum = (ord(sn[0].upper()) - ord("A") + 10) * 10000 + int(sn[1:] or 0)
+        else:
+            self.satnum = int(sn) if sn.isdigit() else 0
+        self.epochyr = int(l1[18:20])
+        self.epochdays = float(l1[20:32])
+        self.ndot = float(l1[33:43]) * (2.0 * math.pi) / (1440.0 * 1440.0)  # satrec.zig:420-424
+        el = np.zeros(10)
+        check(lib().astroz_cuda_sgp4_elements(self._h, dptr(el)))
+        (self.ecco, self.inclo, self.nodeo, self.argpo, self.mo, self.no_kozai, self.bstar, self.a, self.no_unkozai,
+         _) = el.tolist()
+        self.alta = self.a * (1.0 + self.ecco) - 1.0
+        self.altp = self.a * (1.0 - self.ecco) - 1.0
 
     def __del__(self):
         if self._free is not None and self._h:
@@ -125,6 +144,16 @@ class Satrec:
             check(rc)
         return np.zeros(n, dtype=np.uint8), out[:, :3], out[:, 3:]
 
+    def sgp4_array_into(self, jd, fr, positions, velocities) -> None:
+        """Native `Satrec.sgp4_array_into(jd, fr, r, v)` (bindings/python/src/satrec.zig:256-343): fills caller-owned
+        (n, 3) float64 arrays."""
+        _, r, v = self.sgp4_array(jd, fr)
+        n = r.shape[0]
+        if positions.shape[0] < n or velocities.shape[0] < n:
+            raise ValueError("output arrays too small")  # satrec.zig:290-297
+        positions[:n] = r
+        velocities[:n] = v
+
 
 class SatrecArray:
     """Batch propagator, python-sgp4 `SatrecArray` look-alike (bindings/python/astroz/api.py:183-359).
@@ -142,6 +171,31 @@ class SatrecArray:
     @property
     def num_satellites(self) -> int:
         return self._num_sats
+
+    @property
+    def epochs(self) -> list:
+        """Epoch Julian date of each satellite (bindings/python/src/satrec.zig:807)."""
+        return self._c.epochs.tolist()
+
+    def propagate_into(self, times, positions, velocities=None, epoch_offsets=None) -> None:
+        """Native `SatrecArray.propagate_into(times, positions, velocities=None, epoch_offsets=None)`
+        (bindings/python/src/satrec.zig:896-988): near-earth members only, tsince = times[t] + epoch_offsets[sat]
+        (zero offsets = minutes since each satellite's own epoch), TEME, written TIME-MAJOR (n_times, n_sats, 3)
+        into caller-owned float64 arrays."""
+        times = as_f64(times)
+        ns, nt = self._c.numSgp4, times.shape[0]
+        need = ns * nt * 3
+        if positions.size < need:
+            raise ValueError("positions array too small")   # satrec.zig:927-930
+        if velocities is not None and velocities.size < need:
+            raise ValueError("velocities array too small")  # satrec.zig:937-941
+        if ns == 0 or nt == 0:
+            return
+        r, v = self._c.propagate_into(times, None, None, epoch_offsets=epoch_offsets, time_major=True,
+                                      want_velocities=velocities is not None)
+        positions.reshape(-1)[:need] = r.reshape(-1)
+        if velocities is not None:
+            velocities.reshape(-1)[:need] = v.reshape(-1)
 
     def sgp4(self, jd, fr, *, velocities: bool = True):
         jd, fr = as_f64(jd), as_f64(fr)

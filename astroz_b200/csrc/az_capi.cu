@@ -432,6 +432,7 @@ struct Sgp4Single {
     Constellation *c = nullptr;
     double epochJd = 0;
     bool deep = false;
+    double elements[10] = {};  // ecco inclo nodeo argpo mo no_kozai bstar a no_unkozai epochJd
 };
 
 }  // namespace
@@ -1064,7 +1065,23 @@ int32_t astroz_cuda_sgp4_init(const char *line1, const char *line2, int32_t grav
     s->c = static_cast<Constellation *>(ch);
     s->epochJd = s->c->cat.epochs[0];
     s->deep = s->c->cat.nSdp4 == 1;
+    {  // mean elements for the python-sgp4 attribute getters (bindings/python/src/satrec.zig:395-470)
+        az::TleRecord t;
+        az::NearEarth ne;
+        double period = 0.0, perigee = 0.0;
+        if (az::parse_tle(line1, line2, t) == az::kOk &&
+            az::build_common(t, az::gravity(grav), ne, period, perigee) == az::kOk) {
+            const double e[10] = {ne.ecco, ne.inclo, ne.nodeo, ne.argpo, ne.mo, ne.no_kozai, ne.bstar, ne.a, ne.no, ne.epochJd};
+            std::memcpy(s->elements, e, sizeof e);
+        }
+    }
     *out = s;
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_sgp4_elements(astroz_sgp4_t h, double *out10) {
+    if (!h || !out10) return ASTROZ_NULL_POINTER;
+    std::memcpy(out10, static_cast<Sgp4Single *>(h)->elements, sizeof(double) * 10);
     return ASTROZ_OK;
 }
 

@@ -215,6 +215,10 @@ void astroz_cuda_sgp4_free(astroz_sgp4_t h);
 /* 1 if the object is propagated with SDP4 (Satrec.is_deep_space) */
 int32_t astroz_cuda_sgp4_is_deep_space(astroz_sgp4_t h);
 int32_t astroz_cuda_sgp4_epoch(astroz_sgp4_t h, double *epoch_jd);
+/* Mean elements behind the python-sgp4 attribute getters of Satrec (bindings/python/src/satrec.zig:395-470):
+ * out[10] = ecco, inclo, nodeo, argpo, mo (rad), no_kozai (rad/min), bstar, a (un-Kozai'd semi-major axis, earth
+ * radii: Sgp4.Elements.a, src/Sgp4.zig:206-228), no_unkozai (rad/min), epoch JD. */
+int32_t astroz_cuda_sgp4_elements(astroz_sgp4_t h, double *out10);
 /* one time: pos[3] km, vel[3] km/s (TEME) */
 int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3], double vel[3]);
 /* count times (minutes since epoch); results[count][6] = x y z vx vy vz (src/c_api/sgp4.zig:60-100) */

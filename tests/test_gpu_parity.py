@@ -599,3 +599,46 @@ def test_device_side_element_init_large_and_errors(az, synth):
     assert b"element set 3000 " in az.lib().astroz_cuda_last_error()
     empty = az.Constellation.from_device_elements(torch.empty((8, 0), dtype=torch.float64, device="cuda"))
     assert empty.numSatellites == 0
+
+
+def test_python_sgp4_attribute_surface(az, oracle):
+    """Attributes / methods of the native Satrec and SatrecArray the reference exposes beyond sgp4():
+    bindings/python/src/satrec.zig:385-494 (getters), :256-343 (sgp4_array_into), :807 (epochs), :896-988
+    (propagate_into)."""
+    import math
+    from astroz_b200.api import Satrec, SatrecArray, WGS72
+    from tests.golden import tles as T
+    l1, l2 = T.ISS
+    s = Satrec.twoline2rv(l1, l2, WGS72)
+    assert s.satnum == 25544 and s.epochyr == 24 and abs(s.epochdays - 127.82853009) < 1e-12
+    assert abs(s.ecco - 0.0003580) < 1e-15 and abs(s.inclo - math.radians(51.6393)) < 1e-15
+    assert abs(s.nodeo - math.radians(160.4574)) < 1e-15 and abs(s.argpo - math.radians(140.6673)) < 1e-15
+    assert abs(s.mo - math.radians(205.7250)) < 1e-15 and abs(s.bstar - 0.27310e-3) < 1e-18
+    assert abs(s.no_kozai - 15.50957674 * 2 * math.pi / 1440.0) < 1e-15
+    assert abs(s.ndot - 0.00015698 * 2 * math.pi / 1440.0 ** 2) < 1e-20
+    n_unkozai = s.no_unkozai
+    assert abs(s.a - (0.0743669161331734132 / n_unkozai) ** (2.0 / 3.0)) < 1e-14  # a = (xke / no)^(2/3), src/Sgp4.zig:228
+    assert 1.06 < s.a < 1.07 and abs(n_unkozai / s.no_kozai - 1.0) < 2e-3
+    assert abs(s.alta - (s.a * (1 + s.ecco) - 1)) < 1e-15 and abs(s.altp - (s.a * (1 - s.ecco) - 1)) < 1e-15
+    assert not s.is_deep_space
+    jd = np.full(70, s.jdsatepoch)
+    fr = s.jdsatepochF + np.arange(70) / 1440.0
+    e, r, v = s.sgp4_array(jd, fr)
+    r2, v2 = np.zeros((70, 3)), np.zeros((70, 3))
+    s.sgp4_array_into(jd, fr, r2, v2)
+    assert np.array_equal(r, r2) and np.array_equal(v, v2)
+    sats = [Satrec.twoline2rv(a, b, WGS72) for a, b in (T.ISS, T.SAT55909, T.GEO28626, T.SAT55910)]
+    arr = SatrecArray(sats)
+    assert arr.num_satellites == 4 and len(arr.epochs) == 4
+    assert abs(arr.epochs[0] - (s.jdsatepoch + s.jdsatepochF)) < 1e-9
+    times = np.arange(0.0, 90.0, 1.5)
+    p = np.zeros((len(times), 3, 3))
+    vv = np.zeros((len(times), 3, 3))
+    arr.propagate_into(times, p, vv)      # near-earth members only, minutes since each satellite's own epoch
+    for k, (a, b) in enumerate((T.ISS, T.SAT55909, T.SAT55910)):
+        oo = oracle.Sgp4(a, b, oracle.WGS72)
+        for j in (0, 17, 59):
+            ro, vo = oo.propagate(times[j])
+            assert np.max(np.abs(p[j, k] - ro)) < 1e-6 and np.max(np.abs(vv[j, k] - vo)) < 1e-9
+    with pytest.raises(ValueError):
+        arr.propagate_into(times, np.zeros((3, 3, 3)))
