@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
         "astroz_cuda_constellation_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "astroz_cuda_sgp4_propagate_into": (i32, [vp, dp, u32, dp, dp, dp, i32, C.c_double, i32, vp, u32]),
         "astroz_cuda_sgp4_propagate_into_device": (i32, [vp, dp, u32, dp, vp, vp, i32, C.c_double, i32, vp, u32, vp]),
+        "astroz_cuda_sdp4_propagate_into": (i32, [vp, dp, dp, u32, dp, dp, i32, i32, u32, u32]),
+        "astroz_cuda_sdp4_propagate_into_device": (i32, [vp, dp, dp, u32, vp, vp, i32, i32, u32, u32, vp]),
         "astroz_cuda_sgp4_screen": (i32, [vp, dp, u32, dp, u32, C.c_double, C.c_double, dp, C.POINTER(u32)]),
         "astroz_cuda_constellation_coarse_screen_device": (i32, [vp, vp, u32, u32, i32, C.c_double, vp, vp, vp, u32,
                                                                  C.POINTER(C.c_uint64)]),
@@ -113,7 +115,8 @@ EXPORTS = [
     "astroz_cuda_constellation_propagate_device", "astroz_cuda_constellation_propagate_gather",
     "astroz_cuda_constellation_propagate_device_f32", "astroz_cuda_constellation_reset_carry",
     "astroz_cuda_constellation_synchronize", "astroz_cuda_constellation_last_kernel_ms",
-    "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sgp4_screen",
+    "astroz_cuda_sgp4_propagate_into", "astroz_cuda_sgp4_propagate_into_device", "astroz_cuda_sdp4_propagate_into",
+    "astroz_cuda_sdp4_propagate_into_device", "astroz_cuda_sgp4_screen",
     "astroz_cuda_constellation_coarse_screen_device", "astroz_cuda_sgp4_screen_all", "astroz_cuda_sgp4_init",
     "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch", "astroz_cuda_sgp4_elements",
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",

@@ -212,4 +212,22 @@ class SatrecArray:
         return e, r, v
 
 
-__all__ = ["Satrec", "SatrecArray", "jday", "days2mdhms", "WGS72", "WGS84", "WGS72OLD", "accelerated"]
+def sdp4_batch_propagate_into(satrecs, jd, fr, positions, velocities, output_stride: int = -1, sat_offset: int = 0):
+    """Native `sdp4_batch_propagate_into(satrecs, jd, fr, positions, velocities, output_stride=-1, sat_offset=0)`
+    (bindings/python/src/satrec.zig:505-644): deep-space Satrecs only, TEME, TIME-MAJOR, satellite s written at
+    pos[t, sat_offset + s] of a block with `output_stride` satellites per epoch."""
+    sats = list(satrecs)
+    if not sats:
+        return None
+    for s in sats:
+        if not isinstance(s, Satrec):
+            raise TypeError("All items must be Satrec objects")
+        if not s.is_deep_space:
+            raise ValueError("Satrec at index is not a deep-space (SDP4) object")
+    c = Constellation([(s.line1, s.line2) for s in sats], _grav(sats[0].whichconst))
+    c.propagate_sdp4_into(jd, fr, positions, velocities, outputMode=OutputMode.teme, time_major=True,
+                          output_stride=output_stride, sat_offset=sat_offset)
+    return None
+
+
+__all__ = ["sdp4_batch_propagate_into", "Satrec", "SatrecArray", "jday", "days2mdhms", "WGS72", "WGS84", "WGS72OLD", "accelerated"]

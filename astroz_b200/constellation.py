@@ -262,6 +262,22 @@ class Constellation:
             mask.ctypes.data_as(C.c_void_p) if mask is not None else None, rows))
         return positions, velocities
 
+    def propagate_sdp4_into(self, jd, fr, positions, velocities=None, outputMode: int = OutputMode.teme,
+                            time_major: bool = True, output_stride: int = -1, sat_offset: int = 0) -> None:
+        """Constellation.propagateSdp4Constellation (src/Constellation.zig:611-674): the deep-space members only,
+        member i -> row sat_offset + i of caller-owned float64 blocks with `output_stride` rows (default numSdp4),
+        tsince = (jd + fr - epoch) * 1440."""
+        jd, fr = as_f64(jd), as_f64(fr)
+        nt = jd.shape[0]
+        rows = self.numSdp4 if output_stride is None or output_stride <= 0 else int(output_stride)
+        need = rows * nt * 3
+        for arr in (positions, velocities):
+            if arr is not None and (arr.dtype != np.float64 or not arr.flags.c_contiguous or arr.size < need):
+                raise ValueError("output arrays must be C-contiguous float64 with output_stride*n_times*3 elements")
+        check(lib().astroz_cuda_sdp4_propagate_into(
+            self._h, dptr(jd), dptr(fr), nt, dptr(positions), dptr(velocities) if velocities is not None else None,
+            int(outputMode), int(Layout.timeMajor if time_major else Layout.satelliteMajor), rows, int(sat_offset)))
+
     def screen_conjunction(self, times, target: int, threshold: float = 10.0, epoch_offsets=None,
                            reference_jd: float = 0.0):
         """Sgp4Constellation.screen_conjunction(times, target, threshold, epoch_offsets=, reference_jd=)

@@ -71,7 +71,7 @@ struct Constellation {
     cudaStream_t stream = nullptr, copyStream = nullptr;
     // element tables (resident for the life of the handle)
     DevBuf<double> dTiles, dToff;
-    DevBuf<uint32_t> dSgp4Orig, dSdp4Orig, dIdentity;
+    DevBuf<uint32_t> dSgp4Orig, dSdp4Orig, dIdentity, dSdp4Identity;
     DevBuf<az::Sdp4Sat> dSdp4;
     // per-call time axis: tbase | jdFull | gsin | gcos
     // host staging rotates over kSlots pinned buffers so the host can queue several calls ahead of the GPU
@@ -110,7 +110,7 @@ struct Constellation {
 
     ~Constellation() {
         cudaSetDevice(device);
-        dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release();
+        dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release(); dSdp4Identity.release();
         dSdp4.release(); dTime.release(); dToffCall.release(); dMask.release(); dLattice.release(); dPos.release(); dVel.release();
         dHead.release(); dNext.release(); dPairs.release(); dTIdx.release(); dCount.release();
         for (auto &h : hTimeSlot) if (h) cudaFreeHost(h);
@@ -629,6 +629,105 @@ int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, con
     return rc;
 }
 
+// ---- deep-space members only (Constellation.propagateSdp4Constellation, src/Constellation.zig:611-674) --------
+static int32_t sdp4_into_common(Constellation *c, const double *jd, const double *fr, uint32_t nt, double *dPos,
+                                double *dVel, int mode, int layout, uint32_t outNumSats, uint32_t satOffset,
+                                cudaStream_t s) {
+    const uint32_t nd = c->cat.nSdp4;
+    if (c->dSdp4Identity.cap < nd) {
+        std::vector<uint32_t> ident(nd);
+        for (uint32_t i = 0; i < nd; ++i) ident[i] = i;  // origIndices = sat_offset + i, satrec.zig:628-631
+        AZ_CUDA(c->dSdp4Identity.reserve(nd));
+        AZ_CUDA(cudaMemcpy(c->dSdp4Identity.p, ident.data(), (size_t)nd * 4, cudaMemcpyHostToDevice));
+    }
+    double jdMin, jdMax;
+    int32_t rc = upload_time_axis(c, jd, fr, nt, mode, s, &jdMin, &jdMax);
+    if (rc != ASTROZ_OK) return rc;
+    rc = prepare_deep_space(c, jdMin, jdMax, s);
+    if (rc != ASTROZ_OK) return rc;
+    const size_t tcap = c->dTime.cap / 4;
+    az::GridArgs a;
+    a.g = c->g;
+    a.nTimes = nt;
+    a.outNumSats = outNumSats;
+    a.jdFull = c->dTime.p + tcap;
+    a.gsin = c->dTime.p + 2 * tcap;
+    a.gcos = c->dTime.p + 3 * tcap;
+    const size_t shift = (layout == 0) ? (size_t)satOffset * nt * 3 : (size_t)satOffset * 3;
+    a.pos = dPos + shift;
+    a.vel = dVel ? dVel + shift : nullptr;
+    a.sdp4 = c->dSdp4.p;
+    a.orig = c->dSdp4Identity.p;
+    a.nSats = nd;
+    a.lattice = c->dLattice.p;
+    a.latticeNodes = c->latticeNodes;
+    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    AZ_CUDA(az::launch_sdp4_grid(a, mode, layout, s));
+    AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = true;
+    return ASTROZ_OK;
+}
+
+static int32_t sdp4_into_check(Constellation *c, uint32_t out_num_sats, uint32_t sat_offset, uint32_t *rows) {
+    *rows = out_num_sats ? out_num_sats : c->cat.nSdp4;
+    if (*rows < sat_offset + c->cat.nSdp4) {  // src/Constellation.zig:626-628 reports a short buffer this way
+        g_lastError = "output block smaller than sat_offset + numSdp4 rows";
+        return ASTROZ_DECAYED;
+    }
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_sdp4_propagate_into_device(astroz_constellation_t h, const double *jd, const double *fr,
+                                               uint32_t n_times, double *d_pos, double *d_vel, int32_t mode,
+                                               int32_t layout, uint32_t out_num_sats, uint32_t sat_offset, void *stream) {
+    Constellation *c = static_cast<Constellation *>(h);
+    int32_t rc = check_args(c, jd, fr, d_pos, mode, layout);
+    if (rc != ASTROZ_OK) return rc;
+    if (n_times == 0 || c->cat.nSdp4 == 0) return ASTROZ_OK;
+    uint32_t rows;
+    rc = sdp4_into_check(c, out_num_sats, sat_offset, &rows);
+    if (rc != ASTROZ_OK) return rc;
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
+    return sdp4_into_common(c, jd, fr, n_times, d_pos, d_vel, mode, layout, rows, sat_offset, s);
+}
+
+int32_t astroz_cuda_sdp4_propagate_into(astroz_constellation_t h, const double *jd, const double *fr, uint32_t n_times,
+                                        double *pos, double *vel, int32_t mode, int32_t layout, uint32_t out_num_sats,
+                                        uint32_t sat_offset) {
+    Constellation *c = static_cast<Constellation *>(h);
+    int32_t rc = check_args(c, jd, fr, pos, mode, layout);
+    if (rc != ASTROZ_OK) return rc;
+    const uint32_t nd = c->cat.nSdp4;
+    if (n_times == 0 || nd == 0) return ASTROZ_OK;
+    uint32_t rows;
+    rc = sdp4_into_check(c, out_num_sats, sat_offset, &rows);
+    if (rc != ASTROZ_OK) return rc;
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    // the deep-space rows are computed as a dense block on the device and land in the caller's (possibly wider)
+    // block with one strided copy; rows that belong to other satellites are never touched
+    const size_t dense = (size_t)nd * n_times * 3;
+    AZ_CUDA(c->dPos.reserve(dense));
+    if (vel) AZ_CUDA(c->dVel.reserve(dense));
+    rc = sdp4_into_common(c, jd, fr, n_times, c->dPos.p, vel ? c->dVel.p : nullptr, mode, layout, nd, 0, s);
+    if (rc != ASTROZ_OK) return rc;
+    for (int which = 0; which < (vel ? 2 : 1); ++which) {
+        double *dst = which ? vel : pos;
+        const double *src = which ? c->dVel.p : c->dPos.p;
+        if (layout == 0) {
+            AZ_CUDA(cudaMemcpyAsync(dst + (size_t)sat_offset * n_times * 3, src, dense * 8, cudaMemcpyDeviceToHost, s));
+        } else {
+            AZ_CUDA(cudaMemcpy2DAsync(dst + (size_t)sat_offset * 3, (size_t)rows * 24, src, (size_t)nd * 24,
+                                      (size_t)nd * 24, n_times, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    AZ_CUDA(cudaStreamSynchronize(s));
+    return ASTROZ_OK;
+}
+
 int32_t astroz_cuda_constellation_propagate_device_f32(astroz_constellation_t h, const double *jd, const double *fr,
                                                        uint32_t n_times, double *d_pos, double *d_vel, int32_t phase64,
                                                        void *stream) {
@@ -887,20 +986,40 @@ int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *
         return ASTROZ_VALUE_ERROR;
     }
     AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    if (!satellite_mask) {
+        // every near-earth row is written: compute them as a dense block and place it in the caller's (possibly
+        // wider) block with one strided copy; rows that belong to other satellites are never touched
+        const size_t dense = (size_t)ns * n_times * 3;
+        AZ_CUDA(c->dPos.reserve(dense));
+        if (vel) AZ_CUDA(c->dVel.reserve(dense));
+        rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode, reference_jd,
+                              layout, s, 3, nullptr, ns);
+        if (rc != ASTROZ_OK) return rc;
+        for (int which = 0; which < (vel ? 2 : 1); ++which) {
+            double *dst = which ? vel : pos;
+            const double *src = which ? c->dVel.p : c->dPos.p;
+            if (layout == 0 || rows == ns)
+                AZ_CUDA(cudaMemcpyAsync(dst, src, dense * 8, cudaMemcpyDeviceToHost, s));
+            else
+                AZ_CUDA(cudaMemcpy2DAsync(dst, (size_t)rows * 24, src, (size_t)ns * 24, (size_t)ns * 24, n_times,
+                                          cudaMemcpyDeviceToHost, s));
+        }
+        AZ_CUDA(cudaStreamSynchronize(s));
+        return ASTROZ_OK;
+    }
+    // masked rows must keep the caller's contents: stage the caller's block, overwrite the active rows, copy back
     const size_t total = (size_t)rows * n_times * 3;
     AZ_CUDA(c->dPos.reserve(total));
     if (vel) AZ_CUDA(c->dVel.reserve(total));
-    const bool partial = satellite_mask != nullptr || rows != ns;
-    if (partial) {  // rows the kernel will not touch must keep the caller's contents
-        AZ_CUDA(cudaMemcpyAsync(c->dPos.p, pos, total * 8, cudaMemcpyHostToDevice, c->stream));
-        if (vel) AZ_CUDA(cudaMemcpyAsync(c->dVel.p, vel, total * 8, cudaMemcpyHostToDevice, c->stream));
-    }
+    AZ_CUDA(cudaMemcpyAsync(c->dPos.p, pos, total * 8, cudaMemcpyHostToDevice, s));
+    if (vel) AZ_CUDA(cudaMemcpyAsync(c->dVel.p, vel, total * 8, cudaMemcpyHostToDevice, s));
     rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode, reference_jd,
-                          layout, c->stream, 3, satellite_mask, rows);
+                          layout, s, 3, satellite_mask, rows);
     if (rc != ASTROZ_OK) return rc;
-    AZ_CUDA(cudaMemcpyAsync(pos, c->dPos.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (vel) AZ_CUDA(cudaMemcpyAsync(vel, c->dVel.p, total * 8, cudaMemcpyDeviceToHost, c->stream));
-    AZ_CUDA(cudaStreamSynchronize(c->stream));
+    AZ_CUDA(cudaMemcpyAsync(pos, c->dPos.p, total * 8, cudaMemcpyDeviceToHost, s));
+    if (vel) AZ_CUDA(cudaMemcpyAsync(vel, c->dVel.p, total * 8, cudaMemcpyDeviceToHost, s));
+    AZ_CUDA(cudaStreamSynchronize(s));
     return ASTROZ_OK;
 }
 

@@ -166,6 +166,19 @@ int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const d
                                                int32_t mode, double reference_jd, int32_t layout,
                                                const uint8_t *satellite_mask, uint32_t out_num_sats, void *stream);
 
+/* stateless deep-space path: replaces Constellation.propagateSdp4Constellation (src/Constellation.zig:611-674) as
+ * called by sdp4_batch_propagate_into (bindings/python/src/satrec.zig:505-644).  Only the SDP4 satellites of `h` take
+ * part, in catalog order: deep-space satellite i -> output row sat_offset + i of a block with out_num_sats rows
+ * (0 = numSdp4), tsince = (jd[t] + fr[t] - epoch) * 1440 (src/Sdp4Batch.zig:199-215).  HOST buffers; rows of other
+ * satellites are not touched. */
+int32_t astroz_cuda_sdp4_propagate_into(astroz_constellation_t h, const double *jd, const double *fr, uint32_t n_times,
+                                        double *pos, double *vel, int32_t mode, int32_t layout, uint32_t out_num_sats,
+                                        uint32_t sat_offset);
+/* device-resident variant (d_pos / d_vel DEVICE pointers to the whole out_num_sats-row block) */
+int32_t astroz_cuda_sdp4_propagate_into_device(astroz_constellation_t h, const double *jd, const double *fr,
+                                               uint32_t n_times, double *d_pos, double *d_vel, int32_t mode,
+                                               int32_t layout, uint32_t out_num_sats, uint32_t sat_offset, void *stream);
+
 /* Fused propagate + single-target conjunction screen: replaces Constellation.screenConstellation
  * (src/Constellation.zig:683-756) as called by Sgp4Constellation.screen_conjunction
  * (bindings/python/src/sgp4.zig).  Near-earth satellites only, tsince = times[t] + epoch_offsets[sat].

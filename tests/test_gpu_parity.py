@@ -642,3 +642,73 @@ def test_python_sgp4_attribute_surface(az, oracle):
             assert np.max(np.abs(p[j, k] - ro)) < 1e-6 and np.max(np.abs(vv[j, k] - vo)) < 1e-9
     with pytest.raises(ValueError):
         arr.propagate_into(times, np.zeros((3, 3, 3)))
+
+
+def test_high_level_frontend_propagate_and_screen(az, oracle):
+    """astroz.propagate / astroz.screen / astroz.Constellation mirrors (bindings/python/astroz/__init__.py:305-660)
+    and the native sdp4_batch_propagate_into (bindings/python/src/satrec.zig:505-644)."""
+    from datetime import datetime, timezone
+    from astroz_b200 import frontend
+    from astroz_b200.api import Satrec, sdp4_batch_propagate_into, WGS72
+    from tests.golden import tles as T
+    order_in = [T.GEO28626, T.ISS, T.HEO09880, T.SAT55909, T.SAT55910, T.GPS20413]
+    text = "\n".join("NAME\n" + a + "\n" + b for a, b in order_in)
+    c = frontend.Constellation(text)
+    near = [T.ISS, T.SAT55909, T.SAT55910]
+    deep = [T.GEO28626, T.HEO09880, T.GPS20413]
+    assert c.num_satellites == 6 and (c._n_sgp4, c._n_sdp4) == (3, 3)
+    start = datetime(2024, 7, 6, 3, 0, 0, tzinfo=timezone.utc)
+    start_jd = 2440587.5 + start.timestamp() / 86400.0
+    times = np.arange(0.0, 200.0, 7.0)
+    pos, vel = frontend.propagate(c, times, start_time=start, output="teme", velocities=True)
+    assert pos.shape == (len(times), 6, 3) and vel.shape == pos.shape
+    for k, (a, b) in enumerate(near):      # rows [0, n_sgp4): tsince = times + (start - epoch) * 1440
+        o = oracle.Sgp4(a, b, oracle.WGS72)
+        off = (start_jd - c.epochs[k]) * 1440.0
+        for j in (0, 11, len(times) - 1):
+            r, v = o.propagate(times[j] + off)
+            assert np.max(np.abs(pos[j, k] - r)) < 1e-6 and np.max(np.abs(vel[j, k] - v)) < 1e-9
+    for k, (a, b) in enumerate(deep):      # rows after them: the deep-space members, filled (unlike the reference)
+        o = oracle.Sdp4(a, b, oracle.WGS72)
+        for j in (0, 11, len(times) - 1):
+            _, r, v = o.propagate(((start_jd + times[j] / 1440.0) - c.epochs[3 + k]) * 1440.0)
+            assert np.max(np.abs(pos[j, 3 + k] - r)) < 2e-5 and np.max(np.abs(vel[j, 3 + k] - v)) < 2e-9
+    # default output is ECEF = Rz(GMST) * TEME (src/Constellation.zig:930-964)
+    ecef = frontend.propagate(c, times, start_time=start)
+    for j in (0, 5, len(times) - 1):
+        g = oracle.julian_to_gmst(start_jd + times[j] / 1440.0)
+        cg, sg = np.cos(g), np.sin(g)
+        x, y = pos[j, :, 0], pos[j, :, 1]
+        assert np.max(np.abs(ecef[j, :, 0] - (cg * x + sg * y))) < 1e-6
+        assert np.max(np.abs(ecef[j, :, 1] - (-sg * x + cg * y))) < 1e-6
+        assert np.max(np.abs(ecef[j, :, 2] - pos[j, :, 2])) < 1e-9
+    # single-target and all-vs-all screens of a pure near-earth catalogue
+    cn = frontend.Constellation("\n".join(a + "\n" + b for a, b in near))
+    dist, tidx = frontend.screen(cn, times, threshold=5000.0, target=0, start_time=start)
+    pn = frontend.propagate(cn, times, start_time=start, output="teme")
+    d = np.linalg.norm(pn - pn[:, :1], axis=2)
+    assert np.allclose(dist[1:], d.min(axis=0)[1:], atol=1e-6) and np.array_equal(tidx[1:], d.argmin(axis=0)[1:])
+    pairs, tt = frontend.screen(cn, times, threshold=8000.0, start_time=start)
+    want = {(t, i, j) for t in range(len(times)) for i in range(3) for j in range(i + 1, 3)
+            if np.linalg.norm(pn[t, i] - pn[t, j]) < 8000.0}
+    assert {(int(t), int(min(p)), int(max(p))) for p, t in zip(pairs, tt)} == want
+    # the mixed catalogue goes through propagate + the cell-list screen
+    pairs_m, tt_m = frontend.screen(c, times, threshold=9000.0, start_time=start)
+    want_m = {(t, i, j) for t in range(len(times)) for i in range(6) for j in range(i + 1, 6)
+              if np.linalg.norm(pos[t, i] - pos[t, j]) < 9000.0}
+    assert {(int(t), int(min(p)), int(max(p))) for p, t in zip(pairs_m, tt_m)} == want_m
+    # sdp4_batch_propagate_into: time-major, strided, offset rows; other rows untouched
+    sats = [Satrec.twoline2rv(a, b, WGS72) for a, b in deep]
+    jd = np.full(len(times), np.floor(start_jd) + 0.5)
+    fr = (start_jd - jd[0]) + times / 1440.0
+    p2 = np.full((len(times), 7, 3), -1.0)
+    v2 = np.full((len(times), 7, 3), -1.0)
+    sdp4_batch_propagate_into(sats, jd, fr, p2, v2, output_stride=7, sat_offset=2)
+    assert np.all(p2[:, :2] == -1.0) and np.all(p2[:, 5:] == -1.0) and np.all(v2[:, :2] == -1.0)
+    for k, (a, b) in enumerate(deep):
+        o = oracle.Sdp4(a, b, oracle.WGS72)
+        for j in (0, 9, len(times) - 1):
+            _, r, v = o.propagate(((jd[j] + fr[j]) - c.epochs[3 + k]) * 1440.0)
+            assert np.max(np.abs(p2[j, 2 + k] - r)) < 2e-5 and np.max(np.abs(v2[j, 2 + k] - v)) < 2e-9
+    with pytest.raises(ValueError):
+        sdp4_batch_propagate_into([Satrec.twoline2rv(*T.ISS, WGS72)], jd, fr, p2, v2)
