@@ -56,7 +56,7 @@ template <int kN>
 AZ_HD void rotate_small_n(const double (&s0)[kN], const double (&c0)[kN], const double (&d)[kN], double (&s)[kN],
                           double (&c)[kN]) {
     bool big = false;
-    AZ_LANES big |= fabs(d[k]) > AZK(microLimit);
+    AZ_LANES big |= abs_gt(d[k], kHiMicro);
     if (!big) {
         AZ_LANES {
             double sd, cd;
@@ -98,14 +98,14 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
             const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
             const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
             double d = (esine - eps[k]) * rcp_fast(1.0 - ecose);
-            d = fmin(fmax(d, -AZK(clamp)), AZK(clamp));
+            d = clamp_abs(d, kHiClamp, AZK(clamp));
             eps[k] += d;
             delta[k] = d;
-            const double ad = fabs(d);
-            big |= ad > AZK(tinyLimit);
-            linear &= ad < AZK(linearLimit);
-            // Newton's residual after this step is ~ (e/2) delta^2 (f'' = e sin E)
-            done &= d * d * em[k] < AZK(keplerTol);
+            big |= abs_gt(d, kHiTiny);
+            linear &= abs_lt(d, kHiLinear);
+            // Newton's residual after this step is ~ (e/2) delta^2 (f'' = e sin E); it is bounded through the exponent
+            // fields, |d| < 2^(xd-1022) and em < 2^(xe-1022): em d^2 < 2^-49 (1.8e-15 rad) whenever 2 xd + xe <= 3017
+            done &= 2 * expo(d) + expo(em[k]) <= 3017;
         }
         if (linear) {  // |delta| < 1e-8: first-order update is exact to 5e-17 and the solve is finished
             AZ_LANES {
@@ -231,7 +231,7 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
             tho[k] = fma(omgcof, t[k], delm);
             mm[k] = xmdf[k] + tho[k];
             argpm[k] -= tho[k];
-            big |= fabs(tho[k]) > AZK(quarterLimit);
+            big |= abs_gt(tho[k], kHiQuarter);
         }
         AZ_LANES {
             // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle, rotate instead of a second reduction
@@ -255,7 +255,7 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
         a0.con41 = col(kCon41); a0.x1mth2 = col(kX1mth2); a0.x7thm1 = col(kX7thm1);
         AZ_LANES {
             am[k] = abase * tempa[k] * tempa[k];
-            em[k] = fmax(ecco - tempe[k], AZK(emFloor));
+            em[k] = floor_at(ecco - tempe[k], kHiEmFloor, AZK(emFloor));
             mm[k] = fma(no, templ[k], mm[k]);
             sa[k] = a0;
         }
