@@ -19,6 +19,9 @@ enum Sgp4Col : int {
     kMo, kMdot, kArgpo, kArgpdot, kNodeo, kNodedot, kXnodcf, kCc1, kBc4, kT2cof,
     kOmgcof, kEta, kXmcof, kDelmo, kD2, kD3, kD4, kBc5, kSinmao, kT3cof, kT4cof, kT5cof,
     kAbase, kEcco, kNo, kAycof, kXlcof, kCon41, kX1mth2, kX7thm1, kSinio, kCosio, kIsimp,
+    // products of the inclination terms with the literal factors of the short-period block (src/Sgp4.zig:722-740),
+    // folded once per satellite instead of once per cell
+    kMrtA, kMrtB, kDsuK, kNodeK, kDincK, kRvK,
     kSgp4Cols
 };
 constexpr int kSgp4TileDoubles = kSgp4Cols * kTileSats;
@@ -26,7 +29,7 @@ constexpr int kSgp4TileBytes = kSgp4TileDoubles * 8;
 static_assert(kSgp4TileBytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 
 struct GravConsts {  // per-model scalars (kernel parameter -> constant bank)
-    double j2, radiusEarthKm, vkmpersec, j3oj2, xke;
+    double j2, radiusEarthKm, vkmpersec, j3oj2, xke, halfJ2;
 };
 
 struct CellOut {
@@ -49,7 +52,16 @@ struct CellOut {
 #define AZ_LANES _Pragma("unroll") for (int k = 0; k < kN; ++k)
 
 struct SatAngles {  // inclination-dependent per-satellite (SGP4) or per-cell (SDP4) terms
-    double sinio, cosio, aycof, xlcof, con41, x1mth2, x7thm1;
+    double sinio, cosio, aycof, xlcof, x1mth2;
+    double mrtA, mrtB, dsuK, nodeK, dincK, rvK;  // -1.5 con41, 0.5 x1mth2, -0.25 x7thm1, 1.5 cosio, 1.5 cosio sinio, 1.5 con41
+    AZ_HD void fold(double con41, double x7thm1) {
+        mrtA = -1.5 * con41;
+        mrtB = 0.5 * x1mth2;
+        dsuK = -0.25 * x7thm1;
+        nodeK = 1.5 * cosio;
+        dincK = nodeK * sinio;
+        rvK = 1.5 * con41;
+    }
 };
 
 template <int kN>
@@ -93,7 +105,7 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
 #pragma unroll 1
     for (int it = 0; it < 10; ++it) {  // src/Sgp4.zig:687-694
         double delta[kN];
-        bool big = false, done = true, linear = true;
+        bool big = false, done = true, linear = true, micro = true;
         AZ_LANES {
             const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
             const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
@@ -102,6 +114,7 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
             eps[k] += d;
             delta[k] = d;
             big |= abs_gt(d, kHiTiny);
+            micro &= !abs_gt(d, kHiMicro);
             linear &= abs_lt(d, kHiLinear);
             // Newton's residual after this step is ~ (e/2) delta^2 (f'' = e sin E); it is bounded through the exponent
             // fields, |d| < 2^(xd-1022) and em < 2^(xe-1022): em d^2 < 2^-49 (1.8e-15 rad) whenever 2 xd + xe <= 3017
@@ -115,7 +128,15 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
             }
             break;
         }
-        if (!big) {
+        if (micro) {  // |delta| < 2e-3: the usual first step of a near-circular orbit (delta ~ e)
+            AZ_LANES {
+                double sd, cd;
+                sincos_micro(delta[k], sd, cd);
+                const double sn = fma(s[k], cd, c[k] * sd);
+                c[k] = fma(c[k], cd, -(s[k] * sd));
+                s[k] = sn;
+            }
+        } else if (!big) {
             AZ_LANES {
                 double sd, cd;
                 sincos_tiny(delta[k], sd, cd);
@@ -155,17 +176,16 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
         const double cos2u = fma(-2.0 * sinu[k], sinu[k], 1.0);
 
         const double ipl = inv_am[k] * (yb * yb);  // 1 / pl
-        const double temp1 = 0.5 * g.j2 * ipl;
+        const double temp1 = g.halfJ2 * ipl;
         const double temp2 = temp1 * ipl;
         const double w = inv_am[k] * ya[k];  // nm / xke = am^-3/2
-        mrt[k] = fma(rl, fma(-1.5 * temp2 * betal, sa[k].con41, 1.0), 0.5 * temp1 * sa[k].x1mth2 * cos2u);
-        dsu[k] = -0.25 * temp2 * sa[k].x7thm1 * sin2u;
-        const double t2c = 1.5 * temp2 * sa[k].cosio;
-        xnode[k] = fma(t2c, sin2u, nodem[k]);
-        dinc[k] = t2c * sa[k].sinio * cos2u;
+        mrt[k] = fma(rl, fma(temp2 * betal, sa[k].mrtA, 1.0), temp1 * sa[k].mrtB * cos2u);
+        dsu[k] = temp2 * sa[k].dsuK * sin2u;
+        xnode[k] = fma(temp2 * sa[k].nodeK, sin2u, nodem[k]);
+        dinc[k] = temp2 * sa[k].dincK * cos2u;
         const double wt1 = w * temp1;
         mvt[k] = fma(-wt1 * sa[k].x1mth2, sin2u, rdotl);
-        rvdot[k] = fma(wt1, fma(sa[k].x1mth2, cos2u, 1.5 * sa[k].con41), rvdotl);
+        rvdot[k] = fma(wt1, fma(sa[k].x1mth2, cos2u, sa[k].rvK), rvdotl);
     }
 
     double sinsu[kN], cossu[kN], sini[kN], cosi[kN], si0[kN], ci0[kN];
@@ -252,7 +272,9 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
         const double abase = col(kAbase), ecco = col(kEcco), no = col(kNo);
         SatAngles a0;
         a0.sinio = col(kSinio); a0.cosio = col(kCosio); a0.aycof = col(kAycof); a0.xlcof = col(kXlcof);
-        a0.con41 = col(kCon41); a0.x1mth2 = col(kX1mth2); a0.x7thm1 = col(kX7thm1);
+        a0.x1mth2 = col(kX1mth2);
+        a0.mrtA = col(kMrtA); a0.mrtB = col(kMrtB); a0.dsuK = col(kDsuK); a0.nodeK = col(kNodeK);
+        a0.dincK = col(kDincK); a0.rvK = col(kRvK);
         AZ_LANES {
             am[k] = abase * tempa[k] * tempa[k];
             em[k] = floor_at(ecco - tempe[k], kHiEmFloor, AZK(emFloor));
@@ -439,7 +461,8 @@ AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double a
     const double am1[1] = {am}, em1[1] = {em}, mm1[1] = {mm}, ar1[1] = {argpm}, no1[1] = {nodem};
     SatAngles sa[1];
     sa[0].sinio = sinip; sa[0].cosio = cosip; sa[0].aycof = aycof; sa[0].xlcof = xlcof;
-    sa[0].con41 = fma(3.0, cosip2, -1.0); sa[0].x1mth2 = 1.0 - cosip2; sa[0].x7thm1 = fma(7.0, cosip2, -1.0);
+    sa[0].x1mth2 = 1.0 - cosip2;
+    sa[0].fold(fma(3.0, cosip2, -1.0), fma(7.0, cosip2, -1.0));
     CellOut o1[1];
     kepler_posvel<1>(am1, em1, mm1, ar1, no1, sa, g, o1);
     o = o1[0];

@@ -74,6 +74,9 @@ AZ_HD double clamp_abs(double x, uint32_t hiLimit, double limit) {
     const uint32_t h = dbl_hi(x);
     return ((h & 0x7fffffffu) > hiLimit) ? dbl_xor_hi(limit, h & 0x80000000u) : x;
 }
+// x / 2 for a normal x well away from underflow (here: reciprocal square roots of O(1) quantities): one integer
+// subtract on the exponent field instead of a DMUL
+AZ_HD double half_of(double x) { return dbl_with_hi(x, dbl_hi(x) - 0x00100000u); }
 // biased exponent field; |x| < 2^(expo(x) - 1022)
 AZ_HD int expo(double x) { return (int)((dbl_hi(x) >> 20) & 0x7ffu); }
 
@@ -155,18 +158,17 @@ AZ_HD double rsqrt_seed(double x) {
 // 1/sqrt(x), <= 1 ulp
 AZ_HD double rsqrt_nr(double x) {
     double y = rsqrt_seed(x);
-    double hx = 0.5 * x;
-    double e = fma(-hx * y, y, 0.5);  // 0.5 - 0.5 x y^2
-    y = fma(y, e, y);
-    e = fma(-hx * y, y, 0.5);
-    y = fma(y, e, y);
+    double r = fma(-x * y, y, 1.0);  // 1 - x y^2
+    y = fma(half_of(y), r, y);
+    r = fma(-x * y, y, 1.0);
+    y = fma(half_of(y), r, y);
     return y;
 }
 // sqrt(x) from y ~ 1/sqrt(x): one Heron correction
 AZ_HD double sqrt_from_rsqrt(double x, double y) {
     double s = x * y;
     double r = fma(-s, s, x);
-    return fma(0.5 * y, r, s);
+    return fma(half_of(y), r, s);
 }
 AZ_HD double sqrt_(double x) { return sqrt_from_rsqrt(x, rsqrt_nr(x)); }
 

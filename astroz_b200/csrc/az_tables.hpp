@@ -17,7 +17,7 @@
 namespace az {
 
 AZ_EHD inline GravConsts grav_consts(const Gravity &g) {
-    return GravConsts{g.j2, g.radiusEarthKm, g.xke * g.radiusEarthKm / 60.0, g.j3oj2, g.xke};
+    return GravConsts{g.j2, g.radiusEarthKm, g.xke * g.radiusEarthKm / 60.0, g.j3oj2, g.xke, 0.5 * g.j2};
 }
 
 // column values of one near-earth satellite, in Sgp4Col order
@@ -32,6 +32,8 @@ AZ_EHD inline void sgp4_columns(const NearEarth &e, double *c) {
     c[kAbase] = e.aBase; c[kEcco] = e.ecco; c[kNo] = e.no; c[kAycof] = e.aycof; c[kXlcof] = e.xlcof;
     c[kCon41] = e.con41; c[kX1mth2] = e.x1mth2; c[kX7thm1] = e.x7thm1; c[kSinio] = e.sinio; c[kCosio] = e.cosio;
     c[kIsimp] = e.isimp ? 1.0 : 0.0;
+    c[kMrtA] = -1.5 * e.con41; c[kMrtB] = 0.5 * e.x1mth2; c[kDsuK] = -0.25 * e.x7thm1;
+    c[kNodeK] = 1.5 * e.cosio; c[kDincK] = 1.5 * e.cosio * e.sinio; c[kRvK] = 1.5 * e.con41;
 }
 
 AZ_EHD inline Sdp4Sat sdp4_record(const DeepSpace &d) {
