@@ -68,7 +68,8 @@ struct Constellation {
     az::CatalogTables cat;
     az::GravConsts g{};
     double sdp4EpochMin = INFINITY, sdp4EpochMax = -INFINITY;  // epoch span of the deep-space records
-    cudaStream_t stream = nullptr, copyStream = nullptr;
+    cudaStream_t stream = nullptr, copyStream = nullptr, auxStream = nullptr;  // aux: the deep-space grid of a mixed call
+    cudaEvent_t forkEv = nullptr, joinEv = nullptr;
     // element tables (resident for the life of the handle)
     DevBuf<double> dTiles, dToff;
     DevBuf<uint32_t> dSgp4Orig, dSdp4Orig, dIdentity, dSdp4Identity;
@@ -102,9 +103,9 @@ struct Constellation {
     DevBuf<uint32_t> dHead, dNext, dPairs, dTIdx;
     DevBuf<unsigned long long> dCount;
     // kernel timing
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[6] = {};  // K1 start/end, K2 start/end, whole call start/end
     cudaEvent_t chunkDone[64] = {};
-    bool timed = false;
+    bool timed = false, spanTimed = false;
     int variant = -1;  // -1 = shipped default; >= 0 selects a tuning variant (ASTROZ_SGP4_VARIANT)
     int chunks = 8;
 
@@ -121,6 +122,9 @@ struct Constellation {
         for (auto &e : chunkDone) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (copyStream) cudaStreamDestroy(copyStream);
+        if (auxStream) cudaStreamDestroy(auxStream);
+        if (forkEv) cudaEventDestroy(forkEv);
+        if (joinEv) cudaEventDestroy(joinEv);
     }
 };
 
@@ -149,6 +153,9 @@ int32_t open_device(Constellation *c, int device) {
     AZ_CUDA(cudaSetDevice(device));
     AZ_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     AZ_CUDA(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+    AZ_CUDA(cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking));
+    AZ_CUDA(cudaEventCreateWithFlags(&c->forkEv, cudaEventDisableTiming));
+    AZ_CUDA(cudaEventCreateWithFlags(&c->joinEv, cudaEventDisableTiming));
     for (auto &e : c->slotCopied) AZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     AZ_CUDA(cudaEventCreateWithFlags(&c->toffCopied, cudaEventDisableTiming));
     c->timeCopied = c->slotCopied[0];
@@ -356,8 +363,36 @@ int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *
         g_lastError = "internal: satellite-major launches cover the whole time axis";
         return ASTROZ_UNKNOWN;
     }
-    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[0], s));
-    if (L.tileCount && t.nSgp4) {
+    const bool doK1 = L.tileCount && t.nSgp4, doK2 = L.deepSpace && t.nSdp4;
+    // A mixed call runs its two grids side by side: the deep-space grid is small (a few waves of CTAs at lower
+    // fp64-pipe utilisation) and goes first, on the auxiliary stream, so the near-earth CTAs fill the SMs as it drains.
+    const bool fork = doK1 && doK2;
+    cudaStream_t s2 = fork ? c->auxStream : s;
+    if (timeIt) {
+        AZ_CUDA(cudaEventRecord(c->ev[4], s));
+        c->spanTimed = true;
+    }
+    if (fork) {
+        AZ_CUDA(cudaEventRecord(c->forkEv, s));
+        AZ_CUDA(cudaStreamWaitEvent(s2, c->forkEv, 0));
+    }
+    if (!fork && timeIt) AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    if (fork || !doK1) {
+        if (timeIt && !fork) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+        if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[2], s2));
+        if (doK2) {
+            az::GridArgs k2 = a;
+            k2.sdp4 = c->dSdp4.p;
+            k2.orig = c->dSdp4Orig.p;
+            k2.nSats = t.nSdp4;
+            k2.lattice = c->dLattice.p;
+            k2.latticeNodes = c->latticeNodes;
+            AZ_CUDA(az::launch_sdp4_grid(k2, mode, layout, s2));
+        }
+        if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[3], s2));
+    }
+    if (doK1) {
+        if (fork && timeIt) AZ_CUDA(cudaEventRecord(c->ev[0], s));
         az::GridArgs k1 = a;
         k1.sgp4Tiles = c->dTiles.p + (size_t)L.tile0 * az::kSgp4TileDoubles;
         k1.toff = c->dToff.p + (size_t)L.tile0 * az::kTileSats;
@@ -365,19 +400,17 @@ int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *
         const uint32_t first = L.tile0 * az::kTileSats;
         k1.nSats = std::min<uint32_t>(t.nSgp4 - first, L.tileCount * az::kTileSats);
         AZ_CUDA(az::launch_sgp4_grid(k1, mode, layout, s, c->variant));
+        if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+        if (!fork && timeIt) {
+            AZ_CUDA(cudaEventRecord(c->ev[2], s));
+            AZ_CUDA(cudaEventRecord(c->ev[3], s));
+        }
     }
-    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[1], s));
-    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[2], s));
-    if (L.deepSpace && t.nSdp4) {
-        az::GridArgs k2 = a;
-        k2.sdp4 = c->dSdp4.p;
-        k2.orig = c->dSdp4Orig.p;
-        k2.nSats = t.nSdp4;
-        k2.lattice = c->dLattice.p;
-        k2.latticeNodes = c->latticeNodes;
-        AZ_CUDA(az::launch_sdp4_grid(k2, mode, layout, s));
+    if (fork) {
+        AZ_CUDA(cudaEventRecord(c->joinEv, s2));
+        AZ_CUDA(cudaStreamWaitEvent(s, c->joinEv, 0));
     }
-    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[5], s));
     return ASTROZ_OK;
 }
 
@@ -667,6 +700,7 @@ static int32_t sdp4_into_common(Constellation *c, const double *jd, const double
     AZ_CUDA(az::launch_sdp4_grid(a, mode, layout, s));
     AZ_CUDA(cudaEventRecord(c->ev[3], s));
     c->timed = true;
+    c->spanTimed = false;
     return ASTROZ_OK;
 }
 
@@ -756,6 +790,7 @@ int32_t astroz_cuda_constellation_propagate_device_f32(astroz_constellation_t h,
     AZ_CUDA(cudaEventRecord(c->ev[2], s));
     AZ_CUDA(cudaEventRecord(c->ev[3], s));
     c->timed = true;
+    c->spanTimed = false;
     return ASTROZ_OK;
 }
 
@@ -856,6 +891,7 @@ int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const doub
         if (vel) AZ_CUDA(cudaMemcpyAsync(vel + off, dVel + off, cnt * 8, cudaMemcpyDeviceToHost, c->copyStream));
     }
     c->timed = true;
+    c->spanTimed = false;
     AZ_CUDA(cudaStreamSynchronize(c->copyStream));
     AZ_CUDA(cudaStreamSynchronize(s));
     return ASTROZ_OK;
@@ -878,9 +914,16 @@ int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float
     ms[0] = ms[1] = ms[2] = 0.f;
     if (!c->timed) return ASTROZ_NOT_INITIALIZED;
     AZ_CUDA(cudaSetDevice(c->device));
+    AZ_CUDA(cudaEventSynchronize(c->ev[1]));
     AZ_CUDA(cudaEventSynchronize(c->ev[3]));
     AZ_CUDA(cudaEventElapsedTime(&ms[0], c->ev[0], c->ev[1]));
     AZ_CUDA(cudaEventElapsedTime(&ms[2], c->ev[2], c->ev[3]));
+    if (c->spanTimed) {  // the two grids of a mixed call overlap: ms[1] is the span of the whole call
+        AZ_CUDA(cudaEventSynchronize(c->ev[5]));
+        AZ_CUDA(cudaEventElapsedTime(&ms[1], c->ev[4], c->ev[5]));
+    } else {
+        ms[1] = ms[0] + ms[2];
+    }
     return ASTROZ_OK;
 }
 
@@ -950,6 +993,7 @@ static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t 
     AZ_CUDA(cudaEventRecord(c->ev[2], s));
     AZ_CUDA(cudaEventRecord(c->ev[3], s));
     c->timed = true;
+    c->spanTimed = false;
     return ASTROZ_OK;
 }
 
@@ -1079,6 +1123,7 @@ int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, u
     AZ_CUDA(cudaEventRecord(c->ev[2], s));
     AZ_CUDA(cudaEventRecord(c->ev[3], s));
     c->timed = true;
+    c->spanTimed = false;
     AZ_CUDA(cudaMemcpyAsync(out_min_dists, a.minDist, (size_t)ns * 8, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemcpyAsync(out_min_t, a.minT, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaStreamSynchronize(s));
@@ -1335,6 +1380,7 @@ int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *
     AZ_CUDA(cudaEventRecord(c->ev[2], st));
     AZ_CUDA(cudaEventRecord(c->ev[3], st));
     c->timed = true;
+    c->spanTimed = false;
     AZ_CUDA(cudaMemcpyAsync(results, c->dPos.p, (size_t)count * 48, cudaMemcpyDeviceToHost, st));
     AZ_CUDA(cudaStreamSynchronize(st));
     return ASTROZ_OK;

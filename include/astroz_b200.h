@@ -215,7 +215,8 @@ int32_t astroz_cuda_sgp4_screen_all(astroz_constellation_t h, const double *time
 int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h);
 
 /* device time (ms, CUDA events on the launching stream) of the propagation kernels of the last
- * propagate call on this handle: [0] SGP4 grid kernel, [1] SDP4 lattice pre-pass, [2] SDP4 grid kernel */
+ * propagate call on this handle: [0] SGP4 grid kernel, [1] span of all grid launches of the call (the two grids of a
+ * mixed catalog run side by side on two streams, so [1] < [0] + [2] there), [2] SDP4 grid kernel */
 int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float ms[3]);
 
 /* ------------------------------------------------------------------------------------------------
