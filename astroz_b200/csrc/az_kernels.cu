@@ -181,68 +181,78 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
     mbar_wait(&bar, 0);
 
     if constexpr (kLayout == 1 && kGather == 0) {
-        // ---- time-major: for one epoch the tile's 8 satellites are 192 contiguous bytes of the block
-        // (when their output rows are consecutive, i.e. an all-near-earth catalog).  Records are transposed
-        // through shared memory -- [epoch][sat][xyz] -- and leave as 128-bit stores; per-lane 24-byte stores
-        // at a stride of n_sats*24 B measured 2.6x slower with velocities on.
+        // ---- time-major: for one epoch a tile's satellites are consecutive 24-byte records of the block (when
+        // their output rows are consecutive, i.e. an all-near-earth catalog).  Each warp takes PAIRS of adjacent
+        // satellites: a pair's two records are 48 contiguous, 16-byte aligned bytes per epoch, so the warp can
+        // transpose its own 64 epochs x 2 satellites through a private shared-memory patch and emit 128-bit
+        // stores without any CTA-wide barrier (per-lane 24-byte stores at a stride of n_sats*24 B measured 2.6x
+        // slower with velocities on; a CTA-wide 192-byte-row transpose with two barriers per run 11 % slower).
+        // The L2 merges the neighbouring pairs' halves of each 32-byte sector before it is written back.
         constexpr int kRun = 32 * kLanes;
-        __shared__ __align__(16) double tpos[kRun * kTileSats * 3];
-        __shared__ __align__(16) double tvel[kVel ? kRun * kTileSats * 3 : 2];
+        constexpr int kRow = 7;  // 6 doubles per epoch + 1: a 14-word lane stride is bank-conflict free
+        __shared__ __align__(16) double tposAll[kWarps * kRun * kRow];
+        __shared__ __align__(16) double tvelAll[kVel ? kWarps * kRun * kRow : 2];
+        double *tpos = tposAll + warp * kRun * kRow;
+        double *tvel = tvelAll + (kVel ? warp * kRun * kRow : 0);
         const uint32_t sat0 = tileIdx * kTileSats;
-        const uint32_t row0 = __ldg(a.orig + sat0);
         const uint32_t nReal = min((uint32_t)kTileSats, a.nSats - sat0);
-        bool block8 = nReal == kTileSats && a.mask == nullptr && ((((size_t)a.outNumSats * 3) & 1) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(a.pos + (size_t)row0 * 3) & 15u) == 0) &&
-                      (!kVel || (reinterpret_cast<uintptr_t>(a.vel + (size_t)row0 * 3) & 15u) == 0);
-#pragma unroll
-        for (int k = 1; k < kTileSats; ++k) block8 = block8 && (k >= (int)nReal || __ldg(a.orig + sat0 + k) == row0 + k);
+        const bool evenStride = (((size_t)a.outNumSats * 3) & 1) == 0;
 #pragma unroll 1
-        for (uint32_t tw = t0; tw < t1; tw += kRun) {
+        for (int pr = warp; 2 * pr < (int)nReal; pr += kWarps) {
+            const uint32_t satA = sat0 + 2 * pr;
+            const int nPair = min(2, (int)nReal - 2 * pr);
+            const uint32_t rowA = __ldg(a.orig + satA);
+            const bool paired = nPair == 2 && a.mask == nullptr && evenStride && __ldg(a.orig + satA + 1) == rowA + 1 &&
+                                ((reinterpret_cast<uintptr_t>(a.pos + (size_t)rowA * 3) & 15u) == 0) &&
+                                (!kVel || (reinterpret_cast<uintptr_t>(a.vel + (size_t)rowA * 3) & 15u) == 0);
 #pragma unroll 1
-            for (int sl = warp; sl < (int)nReal; sl += kWarps) {
-                const uint32_t sat = sat0 + sl;
-                const double *colBase = tile + sl;
-                auto col = [colBase](int i) { return colBase[i * kTileSats]; };
-                const double toff = __ldg(a.toff + sat);
-                const uint32_t row = __ldg(a.orig + sat);
-                if (a.mask && a.mask[row] == 0) continue;  // laneActive, src/Constellation.zig:530-533 (block8 is off with a mask)
-                double ts[kLanes];
+            for (uint32_t tw = t0; tw < t1; tw += kRun) {
+#pragma unroll 1
+                for (int m = 0; m < nPair; ++m) {
+                    const uint32_t sat = satA + m;
+                    const double *colBase = tile + 2 * pr + m;
+                    auto col = [colBase](int i) { return colBase[i * kTileSats]; };
+                    const double toff = __ldg(a.toff + sat);
+                    const uint32_t row = __ldg(a.orig + sat);
+                    if (a.mask && a.mask[row] == 0) continue;  // laneActive, src/Constellation.zig:530-533
+                    double ts[kLanes];
 #pragma unroll
-                for (int k = 0; k < kLanes; ++k) ts[k] = __ldg(a.tbase + min(tw + 32u * k + lane, t1 - 1)) + toff;
-                CellOut o[kLanes];
-                sgp4_cell<kLanes>(col, ts, a.g, o);
+                    for (int k = 0; k < kLanes; ++k) ts[k] = __ldg(a.tbase + min(tw + 32u * k + lane, t1 - 1)) + toff;
+                    CellOut o[kLanes];
+                    sgp4_cell<kLanes>(col, ts, a.g, o);
 #pragma unroll
-                for (int k = 0; k < kLanes; ++k) {
-                    const uint32_t tk = tw + 32u * k + lane;
-                    if (tk >= t1) continue;
-                    if (a.status) a.status[(size_t)row * a.nTimes + tk] = (o[k].mrt < 1.0) ? 1 : 0;
-                    to_output_frame<kMode, kVel>(a, tk, o[k]);
-                    if (block8) {
-                        double *p = tpos + ((32 * k + lane) * kTileSats + sl) * 3;
-                        p[0] = o[k].rx; p[1] = o[k].ry; p[2] = o[k].rz;
-                        if (kVel) {
-                            double *v = tvel + ((32 * k + lane) * kTileSats + sl) * 3;
-                            v[0] = o[k].vx; v[1] = o[k].vy; v[2] = o[k].vz;
+                    for (int k = 0; k < kLanes; ++k) {
+                        const uint32_t tk = tw + 32u * k + lane;
+                        if (tk >= t1) continue;
+                        if (a.status) a.status[(size_t)row * a.nTimes + tk] = (o[k].mrt < 1.0) ? 1 : 0;
+                        to_output_frame<kMode, kVel>(a, tk, o[k]);
+                        if (paired) {
+                            double *p = tpos + (32 * k + lane) * kRow + m * 3;
+                            p[0] = o[k].rx; p[1] = o[k].ry; p[2] = o[k].rz;
+                            if (kVel) {
+                                double *v = tvel + (32 * k + lane) * kRow + m * 3;
+                                v[0] = o[k].vx; v[1] = o[k].vy; v[2] = o[k].vz;
+                            }
+                        } else {
+                            store_direct<1, kVel>(a, row, tk, o[k]);
                         }
-                    } else {
-                        store_direct<1, kVel>(a, row, tk, o[k]);
                     }
                 }
-            }
-            if (block8) {  // CTA-uniform
-                __syncthreads();
-                const uint32_t count = min((uint32_t)kRun, t1 - tw);           // epochs in this run
-                constexpr int kChunks = kTileSats * 3 / 2;                      // 16-byte chunks per epoch row
-                for (uint32_t i = threadIdx.x; i < count * kChunks; i += kWarps * 32) {
-                    const uint32_t j = i / kChunks, ch = i % kChunks;
-                    const size_t dst = ((size_t)(tw + j) * a.outNumSats + row0) * 3 + 2 * ch;
-                    __stcs(reinterpret_cast<double2 *>(a.pos + dst),
-                           *reinterpret_cast<const double2 *>(tpos + j * kTileSats * 3 + 2 * ch));
-                    if (kVel)
-                        __stcs(reinterpret_cast<double2 *>(a.vel + dst),
-                               *reinterpret_cast<const double2 *>(tvel + j * kTileSats * 3 + 2 * ch));
+                if (paired) {  // warp-uniform
+                    __syncwarp();
+                    const uint32_t count = min((uint32_t)kRun, t1 - tw);  // epochs in this run
+                    for (uint32_t i = lane; i < count * 3; i += 32) {     // three 16-byte chunks per epoch
+                        const uint32_t j = i / 3, ch = i % 3;
+                        const size_t dst = ((size_t)(tw + j) * a.outNumSats + rowA) * 3 + 2 * ch;
+                        const double *sp = tpos + j * kRow + 2 * ch;
+                        __stcs(reinterpret_cast<double2 *>(a.pos + dst), make_double2(sp[0], sp[1]));
+                        if (kVel) {
+                            const double *sv = tvel + j * kRow + 2 * ch;
+                            __stcs(reinterpret_cast<double2 *>(a.vel + dst), make_double2(sv[0], sv[1]));
+                        }
+                    }
+                    __syncwarp();
                 }
-                __syncthreads();
             }
         }
         return;
