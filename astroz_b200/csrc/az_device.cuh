@@ -477,32 +477,64 @@ AZ_HD void eci_to_ecef(double &x, double &y, double sinG, double cosG) {
     y = ey;
 }
 
-// Same fixed point as the reference's iteration lat <- atan2(z + e2 N sin(lat), p) (10 steps, exit at 1e-12,
-// src/WorldCoordinateSystem.zig:98-121), but iterated on (sin lat, cos lat) directly: no trigonometry
-// inside the loop (one rsqrt for N, one for the renormalisation), 6 steps (contraction ~e2 = 6.7e-3 per
-// step from the reference's own starting guess: < 1e-17 rad), then a single atan2 each for lat and lon.
+// Angle of the unit vector (s, c) = (sin a, cos a), a in (-pi, pi]: the fp32 arctangent (idle FMA/XU pipes) is the
+// seed, exactly representable in fp64; one first-order correction with the fp64 sincos of the seed finishes it:
+// d = sin(a - a0) = s cos a0 - c sin a0, |d| < 1e-6, asin(d) - d < 2e-19.  22 fp64 instructions against ~54 for
+// libdevice's atan2 (and no constants to materialise).  The sign of a zero s survives the conversion, so the branch
+// cut at +-pi falls where atan2 puts it.
+AZ_HD double angle_of_unit(double s, double c) {
+    const double a0 = (double)atan2f((float)s, (float)c);
+    double s0, c0;
+    sincos_full(a0, s0, c0);
+    return a0 + fma(s, c0, -(c * s0));
+}
+
+// ECEF -> (geodetic latitude rad, longitude rad, altitude km) on WGS84.  The reference iterates
+// lat <- atan2(z + e2 N sin(lat), p) up to 10 times until the step is below 1e-12 rad
+// (src/WorldCoordinateSystem.zig:98-121); its fixed point is the exact geodetic latitude.  Here the same latitude comes
+// from Bowring's closed form on the parametric latitude u -- tan(lat) = (z + e'^2 b sin^3 u) / (p - e^2 a cos^3 u) --
+// started from his height-corrected u (tan u = (b z / a p)(1 + e'^2 b / r)) and evaluated twice: 2e-13 rad after the
+// first evaluation, rounding level after the second, for 100 km .. 70,000 km altitude at every latitude.  No
+// trigonometry inside: three normalisations (rsqrt) and two angle extractions at the end.  The altitude uses
+// p cos(lat) + z sin(lat) - a sqrt(1 - e2 sin^2(lat)), which equals the reference's p / cos(lat) - N without its
+// cancellation near the poles.
 AZ_HD void ecef_to_geodetic(double &x, double &y, double &z) {
     constexpr double a = 6378.137;
     constexpr double f = 1.0 / 298.257223563;
     constexpr double e2 = 2.0 * f - f * f;
-    const double lon = atan2(y, x);
+    constexpr double b = a * (1.0 - f);
+    constexpr double ep2b = e2 / (1.0 - e2) * b;  // e'^2 b
+    constexpr double e2a = e2 * a;
     const double p2 = fma(x, x, y * y);
-    const double p = sqrt_from_rsqrt(p2, rsqrt_nr(p2));
-    double num = z, den = p * (1.0 - e2);
-    double h = rsqrt_nr(fma(num, num, den * den));
-    double sl = num * h, cl = den * h;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const double N = a * rsqrt_nr(fma(-e2 * sl, sl, 1.0));
-        num = fma(e2 * N, sl, z);
-        h = rsqrt_nr(fma(num, num, p2));
-        sl = num * h;
-        cl = p * h;
+    if (!(p2 > 1.0e-280)) {  // on the polar axis: atan2(0, 0) = 0 for the longitude, like the reference
+        const double az = fabs(z);
+        x = (z < 0.0) ? -0.5 * kPi : 0.5 * kPi;
+        y = 0.0;
+        z = az - b;
+        return;
     }
-    const double N = a * rsqrt_nr(fma(-e2 * sl, sl, 1.0));
-    x = atan2(sl, cl);
+    const double ip = rsqrt_nr(p2);
+    const double p = sqrt_from_rsqrt(p2, ip);
+    const double lon = angle_of_unit(y * ip, x * ip);
+    const double ir = rsqrt_nr(fma(z, z, p2));
+    double su = b * z * fma(ep2b, ir, 1.0), cu = a * p;
+    double num = 0.0, den = 1.0;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double h = rsqrt_nr(fma(su, su, cu * cu));
+        su *= h;
+        cu *= h;
+        num = fma(ep2b * su * su, su, z);
+        den = fma(-e2a * cu * cu, cu, p);
+        su = (1.0 - f) * num;
+        cu = den;
+    }
+    const double h = rsqrt_nr(fma(num, num, den * den));
+    const double sl = num * h, cl = den * h;
+    const double w2 = fma(-e2 * sl, sl, 1.0);
+    x = angle_of_unit(sl, cl);
     y = lon;
-    z = p * rcp(cl) - N;
+    z = fma(p, cl, z * sl) - a * sqrt_from_rsqrt(w2, rsqrt_nr(w2));
 }
 
 }  // namespace az

@@ -99,3 +99,21 @@ def test_geodetic_epilogue_matches_reference_iteration(emul, oracle):
     ref = np.array([oracle.ecef_to_geodetic(e) for e in ecef])
     assert np.max(np.abs(out[:, :2] - ref[:, :2])) < 1e-12
     assert np.max(np.abs(out[:, 2] - ref[:, 2])) < 1e-7
+
+
+def test_geodetic_epilogue_branch_cut_and_axis(emul, oracle):
+    # the longitude branch cut (x < 0, y = +-0 and tiny), the equator, the polar axis
+    dp = C.POINTER(C.c_double)
+    cases = np.array([
+        [-7000.0, 0.0, 100.0], [-7000.0, -0.0, 100.0], [-7000.0, 1e-9, -50.0], [-7000.0, -1e-9, -50.0],
+        [-7000.0, 1e-300, 3.0], [7000.0, 0.0, 0.0], [0.0, 7000.0, 0.0], [0.0, -7000.0, 1.0e-12],
+        [1e-3, -1e-3, 7000.0], [1e-3, 1e-3, -7000.0], [0.0, 0.0, 7000.0], [0.0, 0.0, -6900.0],
+        [4000.0, 4000.0, 42164.0], [-30000.0, 29000.0, -500.0]])
+    out = np.zeros_like(cases)
+    emul.lib.emul_ecef_to_geodetic(np.ascontiguousarray(cases).ctypes.data_as(dp), len(cases), out.ctypes.data_as(dp))
+    ref = np.array([oracle.ecef_to_geodetic(e) for e in cases])
+    assert np.max(np.abs(out[:, :2] - ref[:, :2])) < 1e-12
+    polar = np.abs(np.abs(ref[:, 0]) - np.pi / 2) < 1e-5      # the reference's p / cos(lat) - N loses digits there
+    assert np.max(np.abs(out[~polar, 2] - ref[~polar, 2])) < 1e-7
+    b = 6378.137 * (1.0 - 1.0 / 298.257223563)
+    assert np.allclose(out[polar, 2], np.abs(cases[polar, 2]) - b, atol=1e-6)
