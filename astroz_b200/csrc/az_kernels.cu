@@ -361,6 +361,9 @@ static const Sgp4Variant kVariants[] = {
     {"w2_s256_b4_l2", 2, 256, 4, 2}, {"w4_s768_b3_l2", 4, 768, 3, 2}, {"w4_s768_b2_l3", 4, 768, 2, 3},
     {"w8_s512_b2_l2", 8, 512, 2, 2}, {"w4_s256_b6_l1", 4, 256, 6, 1}, {"w4_s256_b7_l1", 4, 256, 7, 1},
     {"w4_s256_b8_l1", 4, 256, 8, 1}, {"w8_s256_b4_l1", 8, 256, 4, 1}, {"w4_s256_b5_l2", 4, 256, 5, 2},
+    {"w4_s384_b2_l3", 4, 384, 2, 3}, {"w4_s288_b2_l3", 4, 288, 2, 3}, {"w4_s768_b2_l4", 4, 768, 2, 4},
+    {"w4_s512_b2_l4", 4, 512, 2, 4}, {"w8_s768_b1_l3", 8, 768, 1, 3}, {"w4_s384_b3_l3", 4, 384, 3, 3},
+    {"w4_s768_b1_l4", 4, 768, 1, 4}, {"w8_s384_b1_l4", 8, 384, 1, 4},
 };
 int sgp4_variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const char *sgp4_variant_name(int v) { return (v >= 0 && v < sgp4_variant_count()) ? kVariants[v].name : "?"; }
@@ -376,9 +379,14 @@ static cudaError_t launch_k1(const GridArgs &a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Shipped launch shapes (warps per CTA, epochs per stripe, resident CTAs per SM, epochs per thread), from the
+// on-device sweeps in profiles/: the plain satellite-major TEME/ECEF grid likes three epochs per thread (more
+// independent fp64 chains per warp, 158 registers, 2 CTAs/SM: -2.2 %); the time-major transpose and the geodetic
+// epilogue need the registers themselves and are faster with two.
 #ifndef AZ_DEFAULT_K1
-#define AZ_DEFAULT_K1 4, 256, 3, 2
+#define AZ_DEFAULT_K1 4, 384, 2, 3
 #endif
+#define AZ_COMPACT_K1 4, 256, 3, 2
 
 template <int kLayout, int kMode, bool kVel>
 static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int variant) {
@@ -399,10 +407,19 @@ static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int
             case 12: return launch_k1<0, 0, true, 4, 256, 8, 1>(a, stream);
             case 13: return launch_k1<0, 0, true, 8, 256, 4, 1>(a, stream);
             case 14: return launch_k1<0, 0, true, 4, 256, 5, 2>(a, stream);
+            case 15: return launch_k1<0, 0, true, 4, 384, 2, 3>(a, stream);
+            case 16: return launch_k1<0, 0, true, 4, 288, 2, 3>(a, stream);
+            case 17: return launch_k1<0, 0, true, 4, 768, 2, 4>(a, stream);
+            case 18: return launch_k1<0, 0, true, 4, 512, 2, 4>(a, stream);
+            case 19: return launch_k1<0, 0, true, 8, 768, 1, 3>(a, stream);
+            case 20: return launch_k1<0, 0, true, 4, 384, 3, 3>(a, stream);
+            case 21: return launch_k1<0, 0, true, 4, 768, 1, 4>(a, stream);
+            case 22: return launch_k1<0, 0, true, 8, 384, 1, 4>(a, stream);
             default: break;
         }
     }
-    return launch_k1<kLayout, kMode, kVel, AZ_DEFAULT_K1>(a, stream);
+    if constexpr (kLayout == 1 || kMode == 2) return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1>(a, stream);
+    else return launch_k1<kLayout, kMode, kVel, AZ_DEFAULT_K1>(a, stream);
 }
 
 cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant) {
