@@ -243,7 +243,7 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
         const double d2 = col(kD2), d3 = col(kD3), d4 = col(kD4), bc5 = col(kBc5), sinmao = col(kSinmao);
         const double t3cof = col(kT3cof), t4cof = col(kT4cof), t5cof = col(kT5cof);
         double sm[kN], cm[kN], tho[kN];
-        bool big = false;
+        bool big = false, small = true, micro = true;
         AZ_LANES {
             sincos_full(xmdf[k], sm[k], cm[k]);
             const double dm = fma(eta, cm[k], 1.0);
@@ -252,11 +252,16 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
             mm[k] = xmdf[k] + tho[k];
             argpm[k] -= tho[k];
             big |= abs_gt(tho[k], kHiQuarter);
+            small &= !abs_gt(tho[k], kHiTiny);
+            micro &= !abs_gt(tho[k], kHiMicro);
         }
         AZ_LANES {
-            // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle, rotate instead of a second reduction
+            // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle (1e-6 .. 1e-3 rad over days for catalogued objects),
+            // rotate instead of a second reduction, with the shortest series that covers it
             double sd, cd;
-            if (!big) sincos_quarter(tho[k], sd, cd);
+            if (micro) sincos_micro(tho[k], sd, cd);
+            else if (small) sincos_tiny(tho[k], sd, cd);
+            else if (!big) sincos_quarter(tho[k], sd, cd);
             else sincos_full(tho[k], sd, cd);
             const double sinmm = fma(sm[k], cd, cm[k] * sd);
             const double t3 = t2[k] * t[k];
