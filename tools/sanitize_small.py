@@ -20,6 +20,23 @@ ne = Constellation(synth.near_earth_catalog(75))
 t = np.arange(0.0, 200.0, 1.0)
 off = (2460437.5 - ne.epochs) * 1440.0
 ne.propagate_into(t, epoch_offsets=off)
+# time-major with the pair transpose (even and odd row strides), masks, wider blocks
+mask = np.ones(75, dtype=np.uint8)
+mask[[0, 7, 8, 74]] = 0
+for stride in (75, 76, 81):
+    for tm in (True, False):
+        shape = (len(t), stride, 3) if tm else (stride, len(t), 3)
+        p, v = np.zeros(shape), np.zeros(shape)
+        ne.propagate_into(t, p, v, epoch_offsets=off, time_major=tm, output_stride=stride)
+        ne.propagate_into(t, p, v, epoch_offsets=off, satellite_mask=mask, time_major=tm, output_stride=stride)
+# deep-space members only, strided
+pd, vd = np.zeros((len(jd), 210, 3)), np.zeros((len(jd), 210, 3))
+c.propagate_sdp4_into(jd, fr, pd, vd, output_stride=210, sat_offset=5)
+# device-side element init
+import torch
+el = synth.elements_from_tles(tles)
+dv = Constellation.from_device_elements(torch.from_numpy(el).cuda())
+dv.propagate(jd, fr)
 ne.screen_conjunction(t, 3, 100.0, epoch_offsets=off)
 ne.screen_all(t, 50.0, epoch_offsets=off)
 for tle in (G.ISS, G.GEO28626, G.HEO09880):
