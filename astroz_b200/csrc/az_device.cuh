@@ -297,8 +297,13 @@ struct Sdp4Sat {
     double se2, se3, si2, si3, sl2, sl3, sl4, sgh2, sgh3, sgh4, sh2, sh3;  // solar periodics
     double ee2, e3, xi2, xi3, xl2, xl3, xl4, xgh2, xgh3, xgh4, xh2, xh3;  // lunar periodics
     double zmol, zmos, dedt, didt, dmdt, domdt, dnodt;
-    double d2201, d2211, d3210, d3222, d4410, d4422, d5220, d5232, d5421, d5433;
-    double del1, del2, del3, xlamo, xfact, gsto;
+    // Resonance terms d_i sin(phi_b - g_i) folded on the basis angles phi_b (see resonance_accel): the acceleration is
+    // sum_b rp[b] sin(phi_b) + rq[b] cos(phi_b).  Half-day (irez 2) basis: 2w+l, l, w+l, l-w, 2w+2l, 2l, w+2l, 2l-w;
+    // synchronous (irez 1): l, 2l, 3l in the first three slots.
+    double rp[8], rq[8];
+    double xlamo, xfact, gsto;
+    double abase, invNo;       // (xke / no)^(2/3) and 1 / no: the semi-major axis follows no by a short series
+    double sinio, cosio;       // of inclo: the perturbed inclination is a small rotation away
     double epochJd;
     int irez, pad_;
 };
@@ -307,39 +312,47 @@ constexpr double kStepp = 720.0;      // src/Sdp4.zig:51-52
 constexpr double kStep2 = 259200.0;
 constexpr double kRptim = 4.37526908801129966e-3;
 
-// resonance accelerations at (xli, xni, atime)  (src/Sdp4.zig:824-866)
+// resonance accelerations at (xli, xni, atime)  (src/Sdp4.zig:824-866).
+// The reference evaluates ten (half-day) or three (synchronous) sines and cosines of phase-shifted combinations of
+// two angles, w = argpo + argpdot atime and l = xli.  Here sin/cos(w) and sin/cos(l) are the only range-reducing
+// evaluations; the combinations come from angle addition and the constant phases g_i are folded into per-satellite
+// coefficient pairs on the host (sdp4_record): d sin(phi - g) = (d cos g) sin(phi) - (d sin g) cos(phi).
 AZ_HD void resonance_accel(const Sdp4Sat &e, double xli, double xni, double atime, double &xndt, double &xnddt,
                            double &xldot) {
     xldot = xni + e.xfact;
+    double sl, cl;
+    sincos_full(xli, sl, cl);
+    const double s2l = 2.0 * sl * cl, c2l = fma(-2.0 * sl, sl, 1.0);
     if (e.irez == 2) {
-        constexpr double g22 = 5.7686396, g32 = 0.95240898, g44 = 1.8014998, g52 = 1.0508330, g54 = 4.4108898;
-        const double xomi = fma(e.argpdot, atime, e.argpo);
-        const double x2omi = xomi + xomi;
-        const double x2li = xli + xli;
-        double s1, c1, s2, c2, s3, c3, s4, c4, s5, c5, s6, c6, s7, c7, s8, c8, s9, c9, s10, c10;
-        sincos_full(x2omi + xli - g22, s1, c1);
-        sincos_full(xli - g22, s2, c2);
-        sincos_full(xomi + xli - g32, s3, c3);
-        sincos_full(-xomi + xli - g32, s4, c4);
-        sincos_full(x2omi + x2li - g44, s5, c5);
-        sincos_full(x2li - g44, s6, c6);
-        sincos_full(xomi + xli - g52, s7, c7);
-        sincos_full(-xomi + xli - g52, s8, c8);
-        sincos_full(xomi + x2li - g54, s9, c9);
-        sincos_full(-xomi + x2li - g54, s10, c10);
-        xndt = e.d2201 * s1 + e.d2211 * s2 + e.d3210 * s3 + e.d3222 * s4 + e.d4410 * s5 + e.d4422 * s6 +
-               e.d5220 * s7 + e.d5232 * s8 + e.d5421 * s9 + e.d5433 * s10;
-        xnddt = (e.d2201 * c1 + e.d2211 * c2 + e.d3210 * c3 + e.d3222 * c4 + e.d5220 * c7 + e.d5232 * c8 +
-                 2.0 * (e.d4410 * c5 + e.d4422 * c6 + e.d5421 * c9 + e.d5433 * c10)) *
-                xldot;
+        double so, co;
+        sincos_full(fma(e.argpdot, atime, e.argpo), so, co);
+        const double s2o = 2.0 * so * co, c2o = fma(-2.0 * so, so, 1.0);
+        double sb[8], cb[8];
+        rotate(s2o, c2o, sl, cl, sb[0], cb[0]);    // 2w + l
+        sb[1] = sl; cb[1] = cl;                    // l
+        rotate(so, co, sl, cl, sb[2], cb[2]);      // w + l
+        rotate(sl, cl, -so, co, sb[3], cb[3]);     // l - w
+        sb[4] = 2.0 * sb[2] * cb[2]; cb[4] = fma(-2.0 * sb[2], sb[2], 1.0);  // 2w + 2l
+        sb[5] = s2l; cb[5] = c2l;                  // 2l
+        rotate(so, co, s2l, c2l, sb[6], cb[6]);    // w + 2l
+        rotate(s2l, c2l, -so, co, sb[7], cb[7]);   // 2l - w
+        double acc = 0.0, d1 = 0.0, d2 = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            acc = fma(e.rp[b], sb[b], fma(e.rq[b], cb[b], acc));
+            const double dc = fma(e.rp[b], cb[b], -(e.rq[b] * sb[b]));  // d/dphi of the term
+            if (b < 4) d1 += dc;
+            else d2 += dc;
+        }
+        xndt = acc;
+        xnddt = fma(2.0, d2, d1) * xldot;
     } else {
-        constexpr double fasx2 = 0.13130908, fasx4 = 2.8843198, fasx6 = 0.37448087;
-        double s1, c1, s2, c2, s3, c3;
-        sincos_full(xli - fasx2, s1, c1);
-        sincos_full(2.0 * (xli - fasx4), s2, c2);
-        sincos_full(3.0 * (xli - fasx6), s3, c3);
-        xndt = e.del1 * s1 + e.del2 * s2 + e.del3 * s3;
-        xnddt = (e.del1 * c1 + 2.0 * e.del2 * c2 + 3.0 * e.del3 * c3) * xldot;
+        const double s3l = fma(sl, c2l, cl * s2l), c3l = fma(cl, c2l, -(sl * s2l));
+        xndt = fma(e.rp[0], sl, fma(e.rq[0], cl, fma(e.rp[1], s2l, fma(e.rq[1], c2l, fma(e.rp[2], s3l, e.rq[2] * c3l)))));
+        const double dc1 = fma(e.rp[0], cl, -(e.rq[0] * sl));
+        const double dc2 = fma(e.rp[1], c2l, -(e.rq[1] * s2l));
+        const double dc3 = fma(e.rp[2], c3l, -(e.rq[2] * s3l));
+        xnddt = fma(3.0, dc3, fma(2.0, dc2, dc1)) * xldot;
     }
 }
 
@@ -382,6 +395,7 @@ AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double a
     nodem = fma(e.dnodt, t, nodem);
     mm = fma(e.dmdt, t, mm);
     double nm = e.no;
+    double am = e.abase * tempa * tempa;  // (xke / no)^(2/3) tempa^2 (src/Sdp4.zig:913-916 with nm = no)
 
     if (e.irez != 0) {  // final partial step from the lattice node (src/Sdp4.zig:803-819)
         const double ft = t - atime;
@@ -389,14 +403,28 @@ AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double a
         resonance_accel(e, xli, xni, atime, xndt, xnddt, xldot);
         const double nmr = xni + xndt * ft + xnddt * ft * ft * 0.5;
         const double xl = xli + xldot * ft + xndt * ft * ft * 0.5;
-        const double theta = mod_twopi(fma(t, kRptim, e.gsto));
+        // theta = (gsto + t rptim) mod 2pi in the reference; the mean anomaly only ever enters a sine/cosine, whose
+        // range reduction absorbs the multiple of 2pi
+        const double theta = fma(t, kRptim, e.gsto);
         mm = (e.irez == 2) ? xl - 2.0 * nodem + 2.0 * theta : xl - nodem - argpm + theta;
         nm = e.no + (nmr - e.no);
+        if (nm <= 0.0) return 1;
+        // (xke / nm)^(2/3) = abase (1 + x)^(-2/3), x = (nm - no) / no: the resonance libration of the mean motion is a
+        // few 1e-4 of no, so a degree-6 binomial series replaces the reference's division + cube root
+        const double x = (nmr - e.no) * e.invNo;
+        if (abs_gt(x, 0x3f689374u)) {  // |x| > 3e-3 (never seen for catalogued objects): the general evaluation
+            const double cr = cbrt(g.xke / nm);
+            am = cr * cr * tempa * tempa;
+        } else {
+            double p = fma(x, 2618.0 / 6561.0, -308.0 / 729.0);  // binomial coefficients of (1 + x)^(-2/3)
+            p = fma(p, x, 110.0 / 243.0);
+            p = fma(p, x, -40.0 / 81.0);
+            p = fma(p, x, 5.0 / 9.0);
+            p = fma(p, x, -2.0 / 3.0);
+            am *= fma(p, x, 1.0);
+        }
     }
 
-    if (nm <= 0.0) return 1;
-    const double cr = cbrt(g.xke / nm);
-    const double am = cr * cr * tempa * tempa;  // (xke/nm)^(2/3) * tempa^2
     em -= tempe;
     if (em >= 1.0 || em < -0.001) return 2;
     em = fmax(em, 1.0e-6);
@@ -405,9 +433,14 @@ AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double a
 
     // luni-solar periodics, dpper (src/Sdp4.zig:681-759)
     double sz, cz, sinzf, coszf;
+    // zf = zm + 2 ze sin(zm): the second sine/cosine is a rotation of the first by an angle below 2 ze
     double zm = fma(zns, t, e.zmos);
     sincos_full(zm, sz, cz);
-    sincos_full(fma(2.0 * zes, sz, zm), sinzf, coszf);
+    {
+        double sd, cd;
+        sincos_tiny(2.0 * zes * sz, sd, cd);  // |.| <= 0.0335
+        rotate(sz, cz, sd, cd, sinzf, coszf);
+    }
     double f2 = fma(0.5 * sinzf, sinzf, -0.25);
     double f3 = -0.5 * sinzf * coszf;
     double pe = e.se2 * f2 + e.se3 * f3;
@@ -417,7 +450,11 @@ AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double a
     double ph = e.sh2 * f2 + e.sh3 * f3;
     zm = fma(znl, t, e.zmol);
     sincos_full(zm, sz, cz);
-    sincos_full(fma(2.0 * zel, sz, zm), sinzf, coszf);
+    {
+        double sd, cd;
+        sincos_quarter(2.0 * zel * sz, sd, cd);  // |.| <= 0.1098
+        rotate(sz, cz, sd, cd, sinzf, coszf);
+    }
     f2 = fma(0.5 * sinzf, sinzf, -0.25);
     f3 = -0.5 * sinzf * coszf;
     pe += e.ee2 * f2 + e.e3 * f3;
@@ -426,10 +463,17 @@ AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double a
     pgh += e.xgh2 * f2 + e.xgh3 * f3 + e.xgh4 * sinzf;
     ph += e.xh2 * f2 + e.xh3 * f3;
 
+    const double dincl = fma(e.didt, t, pinc);  // inclm - inclo: luni-solar secular + periodic, ~1e-3 rad over years
     inclm += pinc;
     em += pe;
     double sinip, cosip;
-    sincos_full(inclm, sinip, cosip);
+    if (!abs_gt(dincl, kHiTiny)) {
+        double sd, cd;
+        sincos_tiny(dincl, sd, cd);
+        rotate(e.sinio, e.cosio, sd, cd, sinip, cosip);
+    } else {
+        sincos_full(inclm, sinip, cosip);
+    }
     if (inclm >= 0.2) {
         ph = ph * rcp(sinip);
         pgh = fma(-cosip, ph, pgh);

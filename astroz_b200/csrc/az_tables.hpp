@@ -49,9 +49,29 @@ AZ_EHD inline Sdp4Sat sdp4_record(const DeepSpace &d) {
     r.xh3 = d.moon.h3;
     r.zmol = d.zmol; r.zmos = d.zmos; r.dedt = d.dedt; r.didt = d.didt; r.dmdt = d.dmdt; r.domdt = d.domdt;
     r.dnodt = d.dnodt;
-    r.d2201 = d.d2201; r.d2211 = d.d2211; r.d3210 = d.d3210; r.d3222 = d.d3222; r.d4410 = d.d4410;
-    r.d4422 = d.d4422; r.d5220 = d.d5220; r.d5232 = d.d5232; r.d5421 = d.d5421; r.d5433 = d.d5433;
-    r.del1 = d.del1; r.del2 = d.del2; r.del3 = d.del3; r.xlamo = d.xlamo; r.xfact = d.xfact; r.gsto = d.gsto;
+    {   // resonance coefficients folded on their basis angles (resonance_accel, az_device.cuh); phases of src/Sdp4.zig:826-857
+        const double g22 = 5.7686396, g32 = 0.95240898, g44 = 1.8014998, g52 = 1.0508330, g54 = 4.4108898;
+        const double fasx2 = 0.13130908, fasx4 = 2.8843198, fasx6 = 0.37448087;
+        for (int b = 0; b < 8; ++b) r.rp[b] = r.rq[b] = 0.0;
+        if (d.irez == 2) {
+            r.rp[0] = d.d2201 * std::cos(g22);  r.rq[0] = -d.d2201 * std::sin(g22);   // 2w + l
+            r.rp[1] = d.d2211 * std::cos(g22);  r.rq[1] = -d.d2211 * std::sin(g22);   // l
+            r.rp[2] = d.d3210 * std::cos(g32) + d.d5220 * std::cos(g52);              // w + l
+            r.rq[2] = -(d.d3210 * std::sin(g32) + d.d5220 * std::sin(g52));
+            r.rp[3] = d.d3222 * std::cos(g32) + d.d5232 * std::cos(g52);              // l - w
+            r.rq[3] = -(d.d3222 * std::sin(g32) + d.d5232 * std::sin(g52));
+            r.rp[4] = d.d4410 * std::cos(g44);  r.rq[4] = -d.d4410 * std::sin(g44);   // 2w + 2l
+            r.rp[5] = d.d4422 * std::cos(g44);  r.rq[5] = -d.d4422 * std::sin(g44);   // 2l
+            r.rp[6] = d.d5421 * std::cos(g54);  r.rq[6] = -d.d5421 * std::sin(g54);   // w + 2l
+            r.rp[7] = d.d5433 * std::cos(g54);  r.rq[7] = -d.d5433 * std::sin(g54);   // 2l - w
+        } else if (d.irez == 1) {
+            r.rp[0] = d.del1 * std::cos(fasx2);        r.rq[0] = -d.del1 * std::sin(fasx2);        // l
+            r.rp[1] = d.del2 * std::cos(2.0 * fasx4);  r.rq[1] = -d.del2 * std::sin(2.0 * fasx4);  // 2l
+            r.rp[2] = d.del3 * std::cos(3.0 * fasx6);  r.rq[2] = -d.del3 * std::sin(3.0 * fasx6);  // 3l
+        }
+    }
+    r.xlamo = d.xlamo; r.xfact = d.xfact; r.gsto = d.gsto;
+    r.abase = e.aBase; r.invNo = 1.0 / e.no; r.sinio = e.sinio; r.cosio = e.cosio;
     r.epochJd = e.epochJd;
     r.irez = d.irez;
     return r;
