@@ -418,8 +418,16 @@ static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int
             default: break;
         }
     }
-    if constexpr (kLayout == 1 || kMode == 2) return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1>(a, stream);
-    else return launch_k1<kLayout, kMode, kVel, AZ_DEFAULT_K1>(a, stream);
+    if constexpr (kLayout == 1 || kMode == 2) {
+        return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1>(a, stream);
+    } else {
+        // a thread's epochs are 32 apart: short or ragged time axes pad up to 32 * lanes, so take the widest shape
+        // that does not add padded warp-runs (16 epochs x 10^6 Monte-Carlo draws: one lane, not three)
+        const uint32_t runs1 = (a.nTimes + 31) / 32, runs2 = (a.nTimes + 63) / 64 * 2, runs3 = (a.nTimes + 95) / 96 * 3;
+        if (runs3 <= runs2 && runs3 <= runs1) return launch_k1<kLayout, kMode, kVel, AZ_DEFAULT_K1>(a, stream);
+        if (runs2 <= runs1) return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1>(a, stream);
+        return launch_k1<kLayout, kMode, kVel, 4, 256, 4, 1>(a, stream);
+    }
 }
 
 cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant) {

@@ -7,8 +7,6 @@
 
 #include <algorithm>
 #include <cstdint>
-#include <cstdio>
-#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -96,22 +94,6 @@ struct CatalogTables {
     uint32_t sgp4Padded() const { return sgp4Tiles_count() * kTileSats; }
 };
 
-// Host threads worth starting: logical CPUs, narrowed by the container's cgroup CPU quota when there is one (threads
-// beyond the quota are throttled, not run).
-inline uint32_t usable_host_threads() {
-    uint32_t n = std::max(1u, std::thread::hardware_concurrency());
-    if (FILE *f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
-        char quota[32] = {0};
-        double period = 0.0;
-        if (std::fscanf(f, "%31s %lf", quota, &period) == 2 && quota[0] != 'm' && period > 0.0) {
-            const double q = std::atof(quota) / period;
-            if (q >= 1.0) n = std::min<uint32_t>(n, (uint32_t)(q + 0.5));
-        }
-        std::fclose(f);
-    }
-    return n;
-}
-
 // Classify and tabulate parsed element sets.  Returns kOk or the first non-deep-space init failure
 // (src/Constellation.zig:115-126).
 inline int build_catalog_records(const TleRecord *recs, uint32_t n, int gravSel, CatalogTables &out) {
@@ -133,7 +115,7 @@ inline int build_catalog_records(const TleRecord *recs, uint32_t n, int gravSel,
         uint32_t failAt = 0xffffffffu;
     };
     uint32_t nThreads = 1;
-    if (n >= 20000) nThreads = std::min<uint32_t>(usable_host_threads(), std::min<uint32_t>(64, n / 5000));
+    if (n >= 20000) nThreads = std::min<uint32_t>(std::max(1u, std::thread::hardware_concurrency()), std::min<uint32_t>(64, n / 5000));
     std::vector<Chunk> chunks(nThreads);
     auto work = [&](uint32_t k) {
         Chunk &c = chunks[k];
