@@ -10,7 +10,7 @@ namespace az {
 
 // ---- HBM layout of the near-earth element table ----------------------------------------------------
 // Satellite-major tiles: tile k holds satellites [8k, 8k+8) as a [kSgp4Cols][8] block of doubles
-// (2,112 contiguous bytes): SoA inside the tile, so one cp.async.bulk (TMA) lands the whole tile in
+// (2,496 contiguous bytes): SoA inside the tile, so one cp.async.bulk (TMA) lands the whole tile in
 // shared memory and every column chunk is a 64-byte, 128-bit-aligned run.  Only values the kernel
 // reads are stored (the reference's 40-column BatchElements(8) carries 4 splatted constants and a
 // host-only epoch column, src/Sgp4Batch.zig:21-24,71-73); bstar is folded into cc4/cc5 on the host.

@@ -7,7 +7,7 @@
 //                           src/Constellation.zig:448-476)
 //
 // Mapping (K1): a CTA owns one 8-satellite tile of the element table and one stripe of epochs.  The
-// tile (2,112 B, SoA) is staged into shared memory with a single TMA bulk copy (cp.async.bulk +
+// tile (2,496 B, SoA) is staged into shared memory with a single TMA bulk copy (cp.async.bulk +
 // mbarrier).  Each warp takes satellites of the tile in turn; its 32 lanes are 32 consecutive epochs of
 // that satellite, so every per-satellite constant is a conflict-free shared-memory broadcast, the drag
 // model branch (isimp) is warp-uniform, and the Kepler iteration count is near-uniform across the warp
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
 // K1t: one satellite x a long time axis (replaces sgp4Times8 / Sgp4.propagateN, src/simdKernels.zig:21-24,
 // src/Sgp4.zig:753-785; the path behind Satrec.sgp4_array and sgp4_propagate_batch).  With a single
 // satellite K1 would keep one warp per CTA busy; here every thread of every CTA takes epochs of that
-// satellite (kLanes each), its 33 constants sitting in shared memory.
+// satellite (kLanes each), its 39 constants sitting in shared memory.
 constexpr int kTimesThreads = 128;
 constexpr int kTimesLanes = 2;
 template <int kMode, bool kVel>
