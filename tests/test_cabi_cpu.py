@@ -99,3 +99,12 @@ def test_synthetic_catalog_is_valid(oracle):
     mixed = synth.mixed_catalog(400, n_geo=40, n_molniya=20, n_gps=20)
     _, _, _, k2 = oracle.constellation_propagate(mixed, jd, fr)
     assert np.bincount(k2, minlength=4).tolist() == [320, 20, 40, 20]
+
+
+def test_integration_doc_binds_every_export():
+    """INTEGRATION.md shows the reference-side (Zig) extern declaration of every symbol the header declares."""
+    header = open(os.path.join(ROOT, "include", "astroz_b200.h")).read()
+    declared = set(re.findall(r"\b(astroz_cuda_[a-z0-9_]+)\s*\(", header))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    bound = set(re.findall(r"pub extern fn (astroz_cuda_[a-z0-9_]+)\(", doc))
+    assert bound == declared, sorted(declared ^ bound)
