@@ -128,6 +128,16 @@ class Constellation:
     __del__ = deinit
 
     # ---- introspection ------------------------------------------------------------------------
+    @classmethod
+    def from_tle_text(cls, text: str, grav: int = _lib.WGS72, device: int = 0) -> "Constellation":
+        """Name of the native `Sgp4Constellation.from_tle_text` (bindings/python/src/sgp4.zig:287-390)."""
+        return cls.from_text(text, grav, device)
+
+    @property
+    def num_satellites(self) -> int:
+        """`Sgp4Constellation.num_satellites` (bindings/python/src/sgp4.zig:413-420)."""
+        return self.numSatellites
+
     @property
     def epochs(self) -> np.ndarray:
         out = np.empty(self.numSatellites)
