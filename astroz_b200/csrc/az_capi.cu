@@ -110,6 +110,7 @@ struct Constellation {
     int chunks = 8;
 
     ~Constellation() {
+        if (!stream) return;  // never opened on a device (a Satrec that was only inspected): nothing to release
         cudaSetDevice(device);
         dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release(); dSdp4Identity.release();
         dSdp4.release(); dTime.release(); dToffCall.release(); dMask.release(); dLattice.release(); dPos.release(); dVel.release();
@@ -463,6 +464,8 @@ int32_t check_args(Constellation *c, const void *jd, const void *fr, const void 
 
 struct Sgp4Single {
     Constellation *c = nullptr;
+    int device = 0;
+    bool opened = false;  // streams, events and the device tables are created by the first propagation call
     double epochJd = 0;
     bool deep = false;
     double elements[10] = {};  // ecco inclo nodeo argpo mo no_kozai bstar a no_unkozai epochJd
@@ -1217,16 +1220,34 @@ int32_t astroz_cuda_sgp4_screen_all(astroz_constellation_t h, const double *time
 int32_t astroz_cuda_sgp4_init(const char *line1, const char *line2, int32_t grav, int32_t device, astroz_sgp4_t *out) {
     if (!line1 || !line2 || !out) return ASTROZ_NULL_POINTER;
     *out = nullptr;
-    astroz_constellation_t ch = nullptr;
+    // python-sgp4 style code builds thousands of Satrec objects only to hand them to a SatrecArray: parsing and
+    // classification happen here, on the host; device resources come with the first propagation of THIS satellite.
+    {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            g_lastError = "no CUDA device available (this library has no CPU propagation path)";
+            return ASTROZ_NO_DEVICE;
+        }
+        if (device < 0 || device >= count) {
+            g_lastError = "device index out of range";
+            return ASTROZ_VALUE_ERROR;
+        }
+    }
+    Constellation *cc = new (std::nothrow) Constellation();
+    if (!cc) return ASTROZ_ALLOC_FAILED;
     const char *l1[1] = {line1}, *l2[1] = {line2};
-    int32_t rc = astroz_cuda_constellation_create(l1, l2, 1, grav, device, &ch);
-    if (rc != ASTROZ_OK) return rc;
+    const int brc = az::build_catalog(l1, l2, 1, grav, cc->cat);
+    if (brc != az::kOk) {
+        delete cc;
+        return status_to_code(brc);
+    }
     Sgp4Single *s = new (std::nothrow) Sgp4Single();
     if (!s) {
-        astroz_cuda_constellation_free(ch);
+        delete cc;
         return ASTROZ_ALLOC_FAILED;
     }
-    s->c = static_cast<Constellation *>(ch);
+    s->c = cc;
+    s->device = device;
     s->epochJd = s->c->cat.epochs[0];
     s->deep = s->c->cat.nSdp4 == 1;
     {  // mean elements for the python-sgp4 attribute getters (bindings/python/src/satrec.zig:395-470)
@@ -1241,6 +1262,13 @@ int32_t astroz_cuda_sgp4_init(const char *line1, const char *line2, int32_t grav
     }
     *out = s;
     return ASTROZ_OK;
+}
+
+static int32_t ensure_open(Sgp4Single *s) {
+    if (s->opened) return ASTROZ_OK;
+    const int32_t rc = finish_create(s->c, s->device);
+    if (rc == ASTROZ_OK) s->opened = true;
+    return rc;
 }
 
 int32_t astroz_cuda_sgp4_elements(astroz_sgp4_t h, double *out10) {
@@ -1268,6 +1296,10 @@ int32_t astroz_cuda_sgp4_propagate_batch(astroz_sgp4_t h, const double *times, d
     Sgp4Single *s = static_cast<Sgp4Single *>(h);
     if (!s || !times || !results) return ASTROZ_NULL_POINTER;
     if (count == 0) return ASTROZ_OK;
+    {
+        const int32_t orc = ensure_open(s);
+        if (orc != ASTROZ_OK) return orc;
+    }
     Constellation *c = s->c;
     AZ_CUDA(cudaSetDevice(c->device));
     const bool fast = !s->deep && count >= 64;
@@ -1347,6 +1379,10 @@ int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *
     Sgp4Single *s = static_cast<Sgp4Single *>(h);
     if (!s || !jd || !fr || !results) return ASTROZ_NULL_POINTER;
     if (count == 0) return ASTROZ_OK;
+    {
+        const int32_t orc = ensure_open(s);
+        if (orc != ASTROZ_OK) return orc;
+    }
     Constellation *c = s->c;
     if (s->deep || count < 64) {  // deep space / tiny: host-side tsince, then the batch entry point
         std::vector<double> ts(count);

@@ -720,3 +720,23 @@ def test_high_level_frontend_propagate_and_screen(az, oracle):
             assert np.max(np.abs(p2[j, 2 + k] - r)) < 2e-5 and np.max(np.abs(v2[j, 2 + k] - v)) < 2e-9
     with pytest.raises(ValueError):
         sdp4_batch_propagate_into([Satrec.twoline2rv(*T.ISS, WGS72)], jd, fr, p2, v2)
+
+
+def test_many_satrec_objects_are_cheap_until_propagated(az, oracle, synth):
+    """python-sgp4 style: one Satrec per element set, then a SatrecArray over them (benchmarks/python_astroz_bench.py
+    does this for the whole catalogue).  Satrec handles parse and classify on the host and open their device resources
+    lazily, so building thousands of them costs milliseconds, not streams and allocations."""
+    import time
+    from astroz_b200.api import Satrec, SatrecArray, WGS72
+    tles = synth.near_earth_catalog(3000)
+    t0 = time.perf_counter()
+    sats = [Satrec.twoline2rv(a, b, WGS72) for a, b in tles]
+    dt = time.perf_counter() - t0
+    assert dt < 3.0, f"3000 Satrec objects took {dt:.2f} s"
+    assert all(s.error == 0 and not s.is_deep_space for s in sats) and sats[17].satnum == 10017
+    jd, fr = synth.time_grid(90)
+    e, r, v = SatrecArray(sats).sgp4(jd, fr)
+    assert r.shape == (3000, 90, 3) and not e.any()
+    for k in (0, 1234, 2999):     # a lazily opened handle gives the same numbers as the batch
+        e1, r1, v1 = sats[k].sgp4(jd[5], fr[5])
+        assert e1 == 0 and _maxerr(np.array(r1), r[k, 5]) < 1e-9 and _maxerr(np.array(v1), v[k, 5]) < 1e-12
