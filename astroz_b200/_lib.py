@@ -95,6 +95,7 @@ def lib() -> C.CDLL:
         "astroz_cuda_sgp4_propagate_batch": (i32, [vp, dp, dp, u32]),
         "astroz_cuda_sgp4_array": (i32, [vp, dp, dp, C.c_double, dp, u32]),
         "astroz_cuda_fp64_peak": (i32, [i32, dp]),
+        "astroz_cuda_fp64_pipe_peak": (i32, [i32, dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)  # AttributeError here = header/library mismatch: fail loudly
@@ -120,7 +121,7 @@ EXPORTS = [
     "astroz_cuda_constellation_coarse_screen_device", "astroz_cuda_sgp4_screen_all", "astroz_cuda_sgp4_init",
     "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch", "astroz_cuda_sgp4_elements",
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",
-    "astroz_cuda_fp64_peak",
+    "astroz_cuda_fp64_peak", "astroz_cuda_fp64_pipe_peak",
 ]
 
 

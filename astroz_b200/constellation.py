@@ -254,18 +254,40 @@ class Constellation:
         nt = times.shape[0]
         ns = self.numSgp4
         rows = ns if output_stride is None or output_stride <= 0 else int(output_stride)
-        off = np.zeros(ns) if epoch_offsets is None else as_f64(epoch_offsets)[:ns].copy()
+        if rows < ns:
+            raise ValueError("output_stride must be at least num_satellites")
+        if epoch_offsets is None:
+            off = np.zeros(ns)
+        else:
+            off = as_f64(epoch_offsets)
+            if off.shape[0] < ns:
+                raise ValueError("epoch_offsets must have at least num_satellites elements")  # sgp4.zig:144
+            off = off[:ns].copy()
         layout = Layout.timeMajor if time_major else Layout.satelliteMajor
         shape = self._shape(nt, layout, rows=rows)
-        if positions is None:
-            positions = _lib.pinned_empty(shape)
-        if velocities is None and want_velocities:
-            velocities = _lib.pinned_empty(shape)
         mask = None
         if satellite_mask is not None:
             mask = np.ascontiguousarray(satellite_mask, dtype=np.uint8)
             if mask.shape[0] < ns:
                 raise ValueError("satellite_mask must have at least num_satellites elements")  # sgp4.zig:167
+        need = rows * nt * 3
+        for name, arr in (("positions", positions), ("velocities", velocities)):
+            # the C side writes rows*n_times*3 doubles through the raw pointer (satrec.zig:927-941 raises ValueError)
+            if arr is not None and (not isinstance(arr, np.ndarray) or arr.dtype != np.float64 or
+                                    not arr.flags.c_contiguous or not arr.flags.writeable or arr.size < need):
+                raise ValueError(f"{name} must be a writable C-contiguous float64 array with at least "
+                                 f"output_stride*n_times*3 = {need} elements")
+        # rows the mask leaves out, or rows beyond the near-earth satellites, are never written: buffers this
+        # wrapper allocates itself start at zero so the caller never sees uninitialised pinned memory
+        partial = mask is not None or rows > ns
+        if positions is None:
+            positions = _lib.pinned_empty(shape)
+            if partial:
+                positions.fill(0.0)
+        if velocities is None and want_velocities:
+            velocities = _lib.pinned_empty(shape)
+            if partial:
+                velocities.fill(0.0)
         check(lib().astroz_cuda_sgp4_propagate_into(
             self._h, dptr(times), nt, dptr(off), dptr(positions),
             dptr(velocities) if velocities is not None else None, int(outputMode), float(reference_jd), int(layout),
@@ -359,4 +381,11 @@ def fp64_peak_tflops(device: int = 0) -> float:
     """Measured DFMA throughput of the device (the fp64 roofline denominator)."""
     v = C.c_double()
     check(lib().astroz_cuda_fp64_peak(int(device), C.byref(v)))
+    return v.value
+
+
+def fp64_pipe_peak_tflops(device: int = 0) -> float:
+    """Arithmetic peak of the device's fp64 pipe: SMs x 64 lanes x 2 FLOP x max SM clock."""
+    v = C.c_double()
+    check(lib().astroz_cuda_fp64_pipe_peak(int(device), C.byref(v)))
     return v.value

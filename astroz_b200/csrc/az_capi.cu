@@ -1445,5 +1445,19 @@ int32_t astroz_cuda_fp64_peak(int32_t device, double *tflops) {
     return ASTROZ_OK;
 }
 
+int32_t astroz_cuda_fp64_pipe_peak(int32_t device, double *tflops) {
+    if (!tflops) return ASTROZ_NULL_POINTER;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        g_lastError = "no CUDA device available";
+        return ASTROZ_NO_DEVICE;
+    }
+    AZ_CUDA(cudaSetDevice(device));
+    double flops = 0;
+    AZ_CUDA(az::fp64_pipe_peak(&flops));
+    *tflops = flops * 1e-12;
+    return ASTROZ_OK;
+}
+
 #pragma GCC visibility pop
 }  // extern "C"

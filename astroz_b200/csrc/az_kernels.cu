@@ -350,11 +350,13 @@ static cudaError_t launch_k1t(const GridArgs &a, cudaStream_t stream) {
     return cudaGetLastError();
 }
 
+// Launch-shape sweep scaffolding (tools/sweep_variants.py) is compiled only with -DAZ_TUNING; the shipped library
+// carries the chosen shapes alone.
+#ifdef AZ_TUNING
 struct Sgp4Variant {
     const char *name;
     int warps, stripe, minBlocks, lanes;
 };
-// variant 0 is the shipped configuration; the rest exist for on-device tuning sweeps (tools/sweep_variants.py)
 static const Sgp4Variant kVariants[] = {
     {"w4_s256_b4_l1", 4, 256, 4, 1}, {"w4_s256_b3_l2", 4, 256, 3, 2}, {"w4_s512_b3_l2", 4, 512, 3, 2},
     {"w4_s256_b2_l2", 4, 256, 2, 2}, {"w8_s256_b1_l2", 8, 256, 1, 2}, {"w4_s512_b4_l1", 4, 512, 4, 1},
@@ -367,6 +369,10 @@ static const Sgp4Variant kVariants[] = {
 };
 int sgp4_variant_count() { return (int)(sizeof(kVariants) / sizeof(kVariants[0])); }
 const char *sgp4_variant_name(int v) { return (v >= 0 && v < sgp4_variant_count()) ? kVariants[v].name : "?"; }
+#else
+int sgp4_variant_count() { return 0; }
+const char *sgp4_variant_name(int) { return "?"; }
+#endif
 
 template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes, int kGather = 0>
 static cudaError_t launch_k1(const GridArgs &a, cudaStream_t stream) {
@@ -390,6 +396,7 @@ static cudaError_t launch_k1(const GridArgs &a, cudaStream_t stream) {
 
 template <int kLayout, int kMode, bool kVel>
 static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int variant) {
+#ifdef AZ_TUNING
     if (kLayout == 0 && kMode == 0 && kVel) {  // tuning variants exist for the headline specialisation only
         switch (variant) {
             case 0: return launch_k1<0, 0, true, 4, 256, 4, 1>(a, stream);
@@ -418,6 +425,9 @@ static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int
             default: break;
         }
     }
+#else
+    (void)variant;
+#endif
     if constexpr (kLayout == 1 || kMode == 2) {
         return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1>(a, stream);
     } else {
@@ -439,7 +449,7 @@ cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream
         return gv ? launch_k1<0, 0, true, AZ_DEFAULT_K1, 2>(a, stream) : launch_k1<0, 0, false, AZ_DEFAULT_K1, 2>(a, stream);
     }
     const bool vel = a.vel != nullptr;
-    if (a.nSats == 1 && a.nTimes >= 64) {  // single satellite: spread the time axis over the whole GPU
+    if (a.nSats == 1 && a.nTimes >= 64 && a.mask == nullptr) {  // single satellite: spread the time axis over the whole GPU
         // one row: satellite-major and time-major coincide when the block has a single row
         if (layout == 0 || a.outNumSats == 1) {
             if (mode == 0) return vel ? launch_k1t<0, true>(a, stream) : launch_k1t<0, false>(a, stream);
@@ -554,11 +564,13 @@ static cudaError_t launch_k2(const GridArgs &a, cudaStream_t stream) {
     const uint32_t stripes = (a.nTimes + kSdp4Stripe - 1) / kSdp4Stripe;
     if (a.nSats == 0 || stripes == 0) return cudaSuccess;
     dim3 grid(a.nSats, stripes);
+#ifdef AZ_TUNING
     if (kLayout == 0 && kMode == 0 && kVel && kGather == 0 && g_k2Variant >= 0) {
         if (g_k2Variant == 1) { sdp4_grid_kernel<0, 0, true, 0, 4><<<grid, kSdp4Threads, 0, stream>>>(a); return cudaGetLastError(); }
         if (g_k2Variant == 2) { sdp4_grid_kernel<0, 0, true, 0, 5><<<grid, kSdp4Threads, 0, stream>>>(a); return cudaGetLastError(); }
         if (g_k2Variant == 0) { sdp4_grid_kernel<0, 0, true, 0, 3><<<grid, kSdp4Threads, 0, stream>>>(a); return cudaGetLastError(); }
     }
+#endif
     sdp4_grid_kernel<kLayout, kMode, kVel, kGather, AZ_DEFAULT_K2_BLOCKS><<<grid, kSdp4Threads, 0, stream>>>(a);
     return cudaGetLastError();
 }
@@ -812,21 +824,41 @@ cudaError_t launch_sgp4_grid_f32(const GridArgs &a, int phase64, cudaStream_t st
 }
 
 // ---------------------------------------------------------------------------------------------------
-// fp64 roofline denominator: dependent-chain-free DFMA loop, 8 independent accumulators per thread
+// fp64 roofline denominator.  Two figures:
+//   * the pipe's arithmetic peak: SMs x 64 DFMA lanes x 2 FLOP x the maximum SM clock;
+//   * a live DFMA microbenchmark: 8 independent chains per thread, each x = fma(x, a, b) with a, b in the constant bank
+//     (one register source per instruction -- the pattern tools/fp64_probe.cu measured at the pipe's full rate), run
+//     long enough for the clocks to settle (~0.2 s of warm-up), best of 10.
+// bench.py reports the roofline against the larger of the two.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
-    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
-    double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = threadIdx.x * 1e-9 + k;
 #pragma unroll 1
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x[k] = fma(x[k], a, b);
         }
     }
-    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
-    if (s == 1234.5678) out[0] = s;  // keep the chain alive without a real store
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += x[k];
+    if (s == 1234.5678) out[0] = s;  // keep the chains alive without a real store
+}
+
+cudaError_t fp64_pipe_peak(double *flops) {
+    int dev = 0, sms = 0, khz = 0;
+    cudaError_t rc = cudaGetDevice(&dev);
+    if (rc != cudaSuccess) return rc;
+    rc = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (rc != cudaSuccess) return rc;
+    rc = cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev);
+    if (rc != cudaSuccess) return rc;
+    *flops = (double)sms * 64.0 * 2.0 * (double)khz * 1e3;  // sm_100: 64 fp64 FMA lanes per SM
+    return cudaSuccess;
 }
 
 cudaError_t measure_fp64_peak(double *flops) {
@@ -838,12 +870,12 @@ cudaError_t measure_fp64_peak(double *flops) {
     double *d = nullptr;
     rc = cudaMalloc(&d, 8);
     if (rc != cudaSuccess) return rc;
-    const int blocks = sms * 8, threads = 256, iters = 4096;
+    const int blocks = sms * 8, threads = 256, iters = 4096;  // ~4.3 ms per launch at the pipe's peak
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
     float best = 1e30f;
-    for (int rep = 0; rep < 5; ++rep) {
+    for (int rep = 0; rep < 60; ++rep) {
         cudaEventRecord(e0);
         dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
         cudaEventRecord(e1);
@@ -851,7 +883,7 @@ cudaError_t measure_fp64_peak(double *flops) {
         if (rc != cudaSuccess) break;
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        if (rep > 0) best = std::min(best, ms);
+        if (rep >= 50) best = std::min(best, ms);
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);

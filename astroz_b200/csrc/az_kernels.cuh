@@ -97,6 +97,8 @@ cudaError_t launch_sgp4_grid_f32(const GridArgs &a, int phase64, cudaStream_t st
 
 // DFMA throughput microbenchmark: returns achieved fp64 FLOP/s (FMA = 2).
 cudaError_t measure_fp64_peak(double *flops);
+// Arithmetic peak of the fp64 pipe: SMs x 64 lanes x 2 FLOP x the maximum SM clock.
+cudaError_t fp64_pipe_peak(double *flops);
 
 int sgp4_variant_count();
 void set_sdp4_variant(int v);

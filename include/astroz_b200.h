@@ -255,6 +255,9 @@ int32_t astroz_cuda_constellation_propagate_device_f32(astroz_constellation_t h,
 /* ---- measurement helpers --------------------------------------------------------------------- */
 /* DFMA microbenchmark on `device`: achieved fp64 TFLOP/s (FMA = 2) -- the measured roofline denominator */
 int32_t astroz_cuda_fp64_peak(int32_t device, double *tflops);
+/* Arithmetic peak of the fp64 pipe of `device`: SMs x 64 FMA lanes x 2 FLOP x the maximum SM clock, in TFLOP/s.
+ * bench.py reports the roofline against the larger of this and the live microbenchmark. */
+int32_t astroz_cuda_fp64_pipe_peak(int32_t device, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,7 @@
 #include "astroz_oracle.h"
 
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 #include <ctype.h>
@@ -1047,9 +1048,53 @@ static void emit(double *pos, double *vel, size_t ob, int mode, const double r[3
     }
 }
 
-int azo_constellation_propagate(const char *const *l1, const char *const *l2, size_t n, int grav, const double *jd,
-                                const double *fr, size_t nt, double *pos, double *vel, int mode, int layout,
-                                uint8_t *err, int *klass) {
+/* Worker state of azo_constellation_propagate_mt: the satellite loop is independent per satellite (SDP4 carries
+ * couple only along time within one satellite), so threads take contiguous satellite ranges; the arithmetic per
+ * cell is exactly the single-threaded loop's. */
+typedef struct {
+    const azo_sgp4 *sg; const azo_sdp4 *sd; const int *kind;
+    const double *jd, *fr, *gs, *gc;
+    size_t n, nt, i0, stride;
+    double refEpoch;
+    double *pos, *vel;
+    int mode, layout;
+    uint8_t *err;
+} azo_cp_job;
+
+static void *azo_cp_worker(void *arg) {
+    const azo_cp_job *j = (const azo_cp_job *)arg;
+    for (size_t i = j->i0; i < j->n; i += j->stride) {
+        azo_carry carry = { 0.0, 0.0, 0.0 };
+        double off = 0.0;
+        if (j->kind[i] == 0) off = (j->refEpoch - j->sg[i].epochJd) * 1440.0; /* Constellation.zig:153 */
+        else { carry.xli = j->sd[i].xlamo; carry.xni = j->sd[i].s.noUnkozai; }
+        for (size_t t = 0; t < j->nt; t++) {
+            double jdFull = j->jd[t] + j->fr[t];
+            double r[3], v[3];
+            int e = AZO_OK;
+            if (j->kind[i] == 0) {
+                double tsince = (jdFull - j->refEpoch) * 1440.0 + off; /* Constellation.zig:268,425 */
+                azo_sgp4_propagate(&j->sg[i], tsince, r, v);
+            } else {
+                double tsince = (jdFull - j->sd[i].s.epochJd) * 1440.0; /* Constellation.zig:465 */
+                e = azo_sdp4_propagate_carry(&j->sd[i], tsince, &carry, r, v);
+            }
+            size_t ob = out_base(j->layout, i, t, j->nt, j->n);
+            if (e != AZO_OK) { /* zero fill, Constellation.zig:511-528 */
+                j->pos[ob] = j->pos[ob + 1] = j->pos[ob + 2] = 0.0;
+                if (j->vel) j->vel[ob] = j->vel[ob + 1] = j->vel[ob + 2] = 0.0;
+            } else {
+                emit(j->pos, j->vel, ob, j->mode, r, v, j->gs[t], j->gc[t]);
+            }
+            if (j->err) j->err[i * j->nt + t] = (uint8_t)e;
+        }
+    }
+    return NULL;
+}
+
+int azo_constellation_propagate_mt(const char *const *l1, const char *const *l2, size_t n, int grav, const double *jd,
+                                   const double *fr, size_t nt, double *pos, double *vel, int mode, int layout,
+                                   uint8_t *err, int *klass, int threads) {
     azo_sgp4 *sg = (azo_sgp4 *)malloc(sizeof(azo_sgp4) * (n ? n : 1));
     azo_sdp4 *sd = (azo_sdp4 *)malloc(sizeof(azo_sdp4) * (n ? n : 1));
     int *kind = (int *)malloc(sizeof(int) * (n ? n : 1));
@@ -1082,35 +1127,37 @@ int azo_constellation_propagate(const char *const *l1, const char *const *l2, si
         } else { gs[t] = 0.0; gc[t] = 0.0; }
     }
 
-    for (size_t i = 0; i < n; i++) {
-        azo_carry carry = { 0.0, 0.0, 0.0 };
-        double off = 0.0;
-        if (kind[i] == 0) off = (refEpoch - sg[i].epochJd) * 1440.0; /* Constellation.zig:153 */
-        else { carry.xli = sd[i].xlamo; carry.xni = sd[i].s.noUnkozai; }
-        for (size_t t = 0; t < nt; t++) {
-            double jdFull = jd[t] + fr[t];
-            double r[3], v[3];
-            int e = AZO_OK;
-            if (kind[i] == 0) {
-                double tsince = (jdFull - refEpoch) * 1440.0 + off; /* Constellation.zig:268,425 */
-                azo_sgp4_propagate(&sg[i], tsince, r, v);
-            } else {
-                double tsince = (jdFull - sd[i].s.epochJd) * 1440.0; /* Constellation.zig:465 */
-                e = azo_sdp4_propagate_carry(&sd[i], tsince, &carry, r, v);
-            }
-            size_t ob = out_base(layout, i, t, nt, n);
-            if (e != AZO_OK) { /* zero fill, Constellation.zig:511-528 */
-                pos[ob] = pos[ob + 1] = pos[ob + 2] = 0.0;
-                if (vel) vel[ob] = vel[ob + 1] = vel[ob + 2] = 0.0;
-            } else {
-                emit(pos, vel, ob, mode, r, v, gs[t], gc[t]);
-            }
-            if (err) err[i * nt + t] = (uint8_t)e;
+    {
+        if (threads < 1) threads = 1;
+        if (threads > 256) threads = 256;
+        if ((size_t)threads > n) threads = n ? (int)n : 1;
+        azo_cp_job jobs[256];
+        pthread_t tid[256];
+        /* satellites are dealt round-robin so a run of deep-space satellites (slower) spreads over the threads */
+        for (int k = 0; k < threads; k++) {
+            azo_cp_job *j = &jobs[k];
+            j->sg = sg; j->sd = sd; j->kind = kind; j->jd = jd; j->fr = fr; j->gs = gs; j->gc = gc;
+            j->n = n; j->nt = nt; j->refEpoch = refEpoch; j->pos = pos; j->vel = vel; j->mode = mode;
+            j->layout = layout; j->err = err;
+            j->i0 = (size_t)k;
+            j->stride = (size_t)threads;
+        }
+        if (threads == 1) {
+            azo_cp_worker(&jobs[0]);
+        } else {
+            for (int k = 0; k < threads; k++) pthread_create(&tid[k], NULL, azo_cp_worker, &jobs[k]);
+            for (int k = 0; k < threads; k++) pthread_join(tid[k], NULL);
         }
     }
 done:
     free(sg); free(sd); free(kind); free(gs); free(gc);
     return rc;
+}
+
+int azo_constellation_propagate(const char *const *l1, const char *const *l2, size_t n, int grav, const double *jd,
+                                const double *fr, size_t nt, double *pos, double *vel, int mode, int layout,
+                                uint8_t *err, int *klass) {
+    return azo_constellation_propagate_mt(l1, l2, n, grav, jd, fr, nt, pos, vel, mode, layout, err, klass, 1);
 }
 
 int azo_satrec_array_sgp4(const char *const *l1, const char *const *l2, size_t n, int grav, const double *jd,

@@ -103,6 +103,11 @@ int azo_constellation_propagate(const char *const *lines1, const char *const *li
                                 const double *jd, const double *fr, size_t nt,
                                 double *pos, double *vel, int mode, int layout,
                                 uint8_t *err, int *klass);
+/* Same cells, same arithmetic, satellites dealt to `threads` pthreads (full-size parity runs in seconds). */
+int azo_constellation_propagate_mt(const char *const *lines1, const char *const *lines2, size_t n, int grav,
+                                   const double *jd, const double *fr, size_t nt,
+                                   double *pos, double *vel, int mode, int layout,
+                                   uint8_t *err, int *klass, int threads);
 
 /* SatrecArray.sgp4 time model (bindings/python/astroz/api.py:300-302): reference = jd[0]+fr[0]. SGP4 only. */
 int azo_satrec_array_sgp4(const char *const *lines1, const char *const *lines2, size_t n, int grav,

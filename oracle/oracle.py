@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
             C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int, dp, dp, C.c_size_t,
             dp, dp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_int)]
         L.azo_constellation_propagate.restype = C.c_int
+        L.azo_constellation_propagate_mt.argtypes = L.azo_constellation_propagate.argtypes + [C.c_int]
+        L.azo_constellation_propagate_mt.restype = C.c_int
         L.azo_satrec_array_sgp4.argtypes = [
             C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_size_t, C.c_int, dp, dp, C.c_size_t, dp, dp]
         L.azo_satrec_array_sgp4.restype = C.c_int
@@ -190,12 +192,28 @@ def ecef_to_geodetic(ecef) -> np.ndarray:
     return out
 
 
-def constellation_propagate(tles, jd, fr, grav: int = WGS72, mode: int = 0, layout: int = 0, velocities: bool = True):
+def host_threads() -> int:
+    """Threads the host can really run: affinity mask narrowed by the cgroup CPU quota."""
+    n = min(os.cpu_count() or 1, len(os.sched_getaffinity(0)))
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def constellation_propagate(tles, jd, fr, grav: int = WGS72, mode: int = 0, layout: int = 0, velocities: bool = True,
+                            threads: int = 1):
     """Scalar oracle of Constellation.init + propagate (src/Constellation.zig:101-308).
 
     Returns (pos, vel, err[n, nt], klass[n]); pos/vel are shaped by `layout`
-    (0: (n, nt, 3) satellite-major, 1: (nt, n, 3) time-major).
+    (0: (n, nt, 3) satellite-major, 1: (nt, n, 3) time-major).  threads > 1 deals satellites to pthreads
+    (identical arithmetic per cell; used for the full-size BASELINE grids); threads = 0 uses every usable CPU.
     """
+    if threads == 0:
+        threads = host_threads()
     jd = np.ascontiguousarray(jd, dtype=np.float64)
     fr = np.ascontiguousarray(fr, dtype=np.float64)
     n, nt = len(tles), len(jd)
@@ -205,9 +223,9 @@ def constellation_propagate(tles, jd, fr, grav: int = WGS72, mode: int = 0, layo
     err = np.zeros((n, nt), dtype=np.uint8)
     klass = np.zeros(n, dtype=np.int32)
     a1, a2 = _lines(tles)
-    rc = lib().azo_constellation_propagate(
+    rc = lib().azo_constellation_propagate_mt(
         a1, a2, n, grav, _dp(jd), _dp(fr), nt, _dp(pos), _dp(vel) if velocities else None, mode, layout,
-        err.ctypes.data_as(C.POINTER(C.c_uint8)), klass.ctypes.data_as(C.POINTER(C.c_int)))
+        err.ctypes.data_as(C.POINTER(C.c_uint8)), klass.ctypes.data_as(C.POINTER(C.c_int)), int(threads))
     if rc != 0:
         raise ValueError(f"oracle constellation init failed rc={rc}")
     return pos, vel, err, klass

@@ -351,6 +351,127 @@ def test_headline_grid_properties(az, oracle, synth):
     assert np.array_equal(p_host[rows], ph) and np.array_equal(v_host[rows], vh)
 
 
+# ---------------------------------------------------------------------------------------------- BASELINE grids, every cell
+def _report(name, **kw):
+    """Per-config maxima, printed (pytest -s / -rP) and appended to gpurun_out/parity_full.jsonl when that scratch
+    directory exists (profiles/r02_parity_full.jsonl is a committed copy of one such run)."""
+    import json
+    import os
+
+    line = json.dumps({"config": name, **kw})
+    print("parity_full:", line)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_full.jsonl"), "a") as f:
+            f.write(line + "\n")
+
+
+def _device_vs_oracle(dev_block, ref, chunk_rows=2048):
+    """max |device - oracle| over the whole block, streamed through the host in row chunks (the blocks are up to
+    466 MB each; nothing is sampled)."""
+    worst = 0.0
+    for r0 in range(0, ref.shape[0], chunk_rows):
+        got = dev_block[r0:r0 + chunk_rows].cpu().numpy()
+        worst = max(worst, float(np.max(np.abs(got - ref[r0:r0 + chunk_rows]))))
+    return worst
+
+
+def _full_grid_both_layouts(az, oracle, tles, jd, fr, name):
+    """Whole-constellation check in the manner of the reference's own (src/Constellation.zig:784-873), at BASELINE
+    size: EVERY cell of the grid against the scalar oracle, satellite-major and time-major, status bytes included."""
+    import torch
+
+    c = az.Constellation(tles)
+    n, nt = c.numSatellites, len(jd)
+    po, vo, err, klass = oracle.constellation_propagate(tles, jd, fr, threads=0)
+    assert list(c.classes) == list(klass)
+    dev = torch.device("cuda", 0)
+    pos = torch.empty((n, nt, 3), dtype=torch.float64, device=dev)
+    vel = torch.empty_like(pos)
+    status = torch.full((n, nt), 255, dtype=torch.uint8, device=dev)
+    c.propagate_device(jd, fr, pos, vel, status)
+    c.synchronize()
+    dr, dv = _device_vs_oracle(pos, po), _device_vs_oracle(vel, vo)
+    st = status.cpu().numpy()
+    deep = np.asarray(klass) != 0
+    # deep-space cells carry the oracle's codes; near-earth cells flag mrt < 1 (the scalar path's decay check,
+    # src/Sgp4.zig:588-590, which the oracle's near-earth entry reports through its zero-fill only for SDP4)
+    assert np.array_equal(st[deep], err[deep])
+    assert dr < POS_TOL and dv < VEL_TOL, (name, dr, dv)
+    del pos, vel
+    ptm = torch.empty((nt, n, 3), dtype=torch.float64, device=dev)
+    vtm = torch.empty_like(ptm)
+    c.propagate_device(jd, fr, ptm, vtm, layout=1)
+    c.synchronize()
+    dr_t = _device_vs_oracle(ptm.transpose(0, 1), po)
+    dv_t = _device_vs_oracle(vtm.transpose(0, 1), vo)
+    assert dr_t < POS_TOL and dv_t < VEL_TOL, (name, dr_t, dv_t)
+    _report(name, cells=n * nt, n_sgp4=c.numSgp4, n_sdp4=c.numSdp4, max_dr_km=dr, max_dv_kms=dv,
+            max_dr_km_time_major=dr_t, max_dv_kms_time_major=dv_t, failed_cells=int((err != 0).sum()))
+    return c
+
+
+def test_config2_full_grid_every_cell(az, oracle, synth):
+    """BASELINE config 2: 13,478 near-earth satellites (seed 13478) x 1,440 epochs = 19,408,320 cells, all compared."""
+    tles = synth.near_earth_catalog(synth.HEADLINE_SATS, seed=13478)
+    jd, fr = synth.time_grid(1440)
+    c = _full_grid_both_layouts(az, oracle, tles, jd, fr, "config2")
+    assert c.numSdp4 == 0 and c.numSatellites == 13478
+
+
+def test_config3_full_grid_every_cell(az, oracle, synth):
+    """BASELINE config 3: the 13,478-slot catalog with 1,024 GEO + 256 Molniya + 256 GPS-like deep-space members
+    (seed 28626) x 1,440 epochs, all cells, all four classes, status bytes."""
+    tles = synth.mixed_catalog(synth.HEADLINE_SATS, seed=28626, n_geo=1024, n_molniya=256, n_gps=256)
+    jd, fr = synth.time_grid(1440)
+    c = _full_grid_both_layouts(az, oracle, tles, jd, fr, "config3")
+    assert c.numSdp4 == 1536 and set(np.asarray(c.classes).tolist()) == {0, 1, 2, 3}
+
+
+def test_config4_week_grid_strided_epochs(az, oracle, synth):
+    """BASELINE config 4 on one GPU: the whole 13,478 x 10,080 grid (135.9 M cells, 6.5 GB in HBM) is propagated;
+    every 16th epoch out to the end of the week (630 epochs x all satellites = 8.5 M cells) is compared with the
+    oracle.  Horizons beyond one day are pinned by no reference vector: the scalar restatement is
+    the authority here."""
+    import torch
+
+    tles = synth.near_earth_catalog(synth.HEADLINE_SATS, seed=13478)
+    jd, fr = synth.time_grid(10080)
+    c = az.Constellation(tles)
+    n, nt = c.numSatellites, len(jd)
+    dev = torch.device("cuda", 0)
+    pos = torch.empty((n, nt, 3), dtype=torch.float64, device=dev)
+    vel = torch.empty_like(pos)
+    c.propagate_device(jd, fr, pos, vel)
+    c.synchronize()
+    po, vo, err, _ = oracle.constellation_propagate(tles, jd[::16].copy(), fr[::16].copy(), threads=0)
+    dr = _device_vs_oracle(pos[:, ::16], po)
+    dv = _device_vs_oracle(vel[:, ::16], vo)
+    assert torch.isfinite(pos).all() and torch.isfinite(vel).all()
+    assert dr < POS_TOL and dv < VEL_TOL, (dr, dv)
+    _report("config4", cells=n * nt, compared_cells=int(po.shape[0] * po.shape[1]), max_dr_km=dr, max_dv_kms=dv)
+
+
+def test_config5_all_draws_every_cell(az, oracle, synth):
+    """BASELINE config 5: all 10,000 Monte-Carlo draws x 1,440 epochs in fp64, every cell against the oracle."""
+    import torch
+
+    tles = synth.monte_carlo_catalog(10000)
+    jd, fr = synth.time_grid(1440, jd0=2460437.5)
+    c = az.Constellation(tles)
+    assert c.numSgp4 == 10000
+    n, nt = c.numSatellites, len(jd)
+    dev = torch.device("cuda", 0)
+    pos = torch.empty((n, nt, 3), dtype=torch.float64, device=dev)
+    vel = torch.empty_like(pos)
+    c.propagate_device(jd, fr, pos, vel)
+    c.synchronize()
+    po, vo, err, _ = oracle.constellation_propagate(tles, jd, fr, threads=0)
+    dr, dv = _device_vs_oracle(pos, po), _device_vs_oracle(vel, vo)
+    assert dr < POS_TOL and dv < VEL_TOL, (dr, dv)
+    _report("config5", cells=n * nt, max_dr_km=dr, max_dv_kms=dv)
+
+
 # ---------------------------------------------------------------------------------------------- next rows (SURVEY 8f)
 def test_fused_single_target_screen(az, oracle, synth):
     """Constellation.screenConstellation (src/Constellation.zig:683-756) fused on the device: minimum distance
@@ -553,9 +674,27 @@ def test_propagate_into_mask_and_output_stride(az, oracle, synth):
         assert np.all(ps[np.flatnonzero(mask == 0)] == 7.0) and np.all(ps[37:] == 7.0)
     with pytest.raises(ValueError):
         c.propagate_into(times, satellite_mask=np.ones(5, dtype=np.uint8))
+    # caller buffers are validated before the raw pointers reach the C side (satrec.zig:927-941, sgp4.zig:144)
+    good = np.zeros((37, len(times), 3))
+    for bad in (good.astype(np.float32), np.zeros((37, len(times), 6))[:, :, ::2], np.zeros((36, len(times), 3))):
+        with pytest.raises(ValueError):
+            c.propagate_into(times, bad, None, epoch_offsets=off, time_major=False, want_velocities=False)
+        with pytest.raises(ValueError):
+            c.propagate_into(times, good, bad, epoch_offsets=off, time_major=False)
+    with pytest.raises(ValueError):
+        c.propagate_into(times, epoch_offsets=off[:20])
+    # buffers the wrapper allocates itself: masked rows come back as zeros, not uninitialised pinned memory
+    pm, vm = c.propagate_into(times, epoch_offsets=off, satellite_mask=mask, time_major=False)
+    assert np.all(pm[mask == 0] == 0.0) and np.all(vm[mask == 0] == 0.0) and np.array_equal(pm[mask == 1], full_p[mask == 1])
+    # a one-satellite constellation takes the time-parallel kernel only when no mask is given: a masked-out row stays
+    one = az.Constellation(tles[:1])
+    keep = np.full((1, 200, 3), 7.0)
+    one.propagate_into(np.arange(200.0), keep, None, epoch_offsets=np.zeros(1), satellite_mask=np.zeros(1, dtype=np.uint8),
+                       time_major=False, want_velocities=False)
+    assert np.all(keep == 7.0)
 
 
-def test_device_side_element_init_matches_host_init(az, synth):
+def test_device_side_element_init_matches_host_init(az, oracle, synth):
     """K5: element columns resident in HBM -> classification + Sgp4/Sdp4.initElements + table build on the
     device (src/Constellation.zig:101-200, src/Sgp4.zig:108-417, src/Sdp4.zig:174-657).  Must reproduce the host
     ingest: same classes, row maps and reference epoch, and the same trajectories to the device libm's last ulps."""
@@ -577,9 +716,13 @@ def test_device_side_element_init_matches_host_init(az, synth):
             ph, vh = host.propagate(jd, fr, layout=layout)
             pd, vd = dev.propagate(jd, fr, layout=layout)
             assert np.max(np.abs(pd - ph)) < 1e-8 and np.max(np.abs(vd - vh)) < 1e-11
+            # and directly against the oracle (which parses the TLE text the element columns came from)
+            po, vo, _, klass = oracle.constellation_propagate(tles, jd, fr, layout=int(layout), threads=0)
+            assert list(dev.classes) == list(klass)
+            assert _maxerr(pd, po) < POS_TOL and _maxerr(vd, vo) < VEL_TOL
 
 
-def test_device_side_element_init_large_and_errors(az, synth):
+def test_device_side_element_init_large_and_errors(az, oracle, synth):
     import torch
     # more than 1024 blocks of 256 element sets: the block-offset scan carries between its passes
     n = 300_001
@@ -595,6 +738,13 @@ def test_device_side_element_init_large_and_errors(az, synth):
     ph, vh = host.propagate(jd, fr)
     pd, vd = dev.propagate(jd, fr)
     assert np.max(np.abs(pd - ph)) < 1e-8 and np.max(np.abs(vd - vh)) < 1e-11
+    # the 4,096 distinct element sets the draw came from, device-initialised, against the oracle directly
+    base_tles = synth.mixed_catalog(4096, n_geo=300, n_molniya=100, n_gps=100)
+    devb = az.Constellation.from_device_elements(torch.from_numpy(np.ascontiguousarray(base)).cuda())
+    pb, vb = devb.propagate(jd, fr, layout=0)
+    po, vo, _, klass = oracle.constellation_propagate(base_tles, jd, fr, threads=0)
+    assert list(devb.classes) == list(klass)
+    assert _maxerr(pb, po) < POS_TOL and _maxerr(vb, vo) < VEL_TOL
     # the first failing element set in catalog order decides the error (src/Constellation.zig:115-126)
     bad = el[:, :5000].copy()
     bad[2, 4100] = 1.5      # eccentricity >= 1  -> InvalidEccentricity
