@@ -87,6 +87,13 @@ struct Constellation {
     double *hTime = nullptr;          // the slot in use by the current call
     cudaEvent_t timeCopied = nullptr;  // its event
     bool timePending = false;          // kept for call sites: set after recording timeCopied
+    // the time axis last uploaded by upload_time_axis: a repeated call with the same jd/fr (a propagation loop over a
+    // fixed grid) reuses the device copy instead of re-uploading it
+    std::vector<double> cachedJd, cachedFr;
+    bool cachedGmst = false, cacheValid = false;
+    double cachedRef = 0.0, cachedJdMin = 0.0, cachedJdMax = 0.0;
+    cudaEvent_t axisReady = nullptr;   // recorded after the cached axis' upload
+    cudaStream_t axisStream = nullptr;
     // stateless-path epoch offsets
     DevBuf<double> dToffCall;
     DevBuf<uint8_t> dMask;
@@ -119,6 +126,7 @@ struct Constellation {
         if (hToffCall) cudaFreeHost(hToffCall);
         for (auto &e : slotCopied) if (e) cudaEventDestroy(e);
         if (toffCopied) cudaEventDestroy(toffCopied);
+        if (axisReady) cudaEventDestroy(axisReady);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : chunkDone) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
@@ -159,6 +167,7 @@ int32_t open_device(Constellation *c, int device) {
     AZ_CUDA(cudaEventCreateWithFlags(&c->joinEv, cudaEventDisableTiming));
     for (auto &e : c->slotCopied) AZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     AZ_CUDA(cudaEventCreateWithFlags(&c->toffCopied, cudaEventDisableTiming));
+    AZ_CUDA(cudaEventCreateWithFlags(&c->axisReady, cudaEventDisableTiming));
     c->timeCopied = c->slotCopied[0];
     for (auto &ev : c->ev) AZ_CUDA(cudaEventCreate(&ev));
     for (auto &ev : c->chunkDone) AZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -283,6 +292,7 @@ int32_t ingest_on_device(Constellation *c, az::IngestArgs a, int grav) {
 
 // host staging for the time axis; waits for the previous call's async upload before reuse
 int32_t reserve_time(Constellation *c, size_t nt) {
+    c->cacheValid = false;  // every writer of dTime comes through here (or says so itself)
     // the call that last used the current slot recorded slotCopied[slot] (timePending tells us so)
     if (c->timePending) c->slotPending[c->slot] = true;
     c->timePending = false;
@@ -419,6 +429,15 @@ int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *
 // queue its upload on s.
 int32_t upload_time_axis(Constellation *c, const double *jd, const double *fr, uint32_t nt, int mode, cudaStream_t s,
                          double *jdMin, double *jdMax) {
+    if (c->cacheValid && c->cachedJd.size() == nt && c->cachedRef == c->cat.referenceEpochJd &&
+        (mode == 0 || c->cachedGmst) && std::memcmp(c->cachedJd.data(), jd, (size_t)nt * 8) == 0 &&
+        std::memcmp(c->cachedFr.data(), fr, (size_t)nt * 8) == 0) {
+        *jdMin = c->cachedJdMin;
+        *jdMax = c->cachedJdMax;
+        if (s != c->axisStream) AZ_CUDA(cudaStreamWaitEvent(s, c->axisReady, 0));
+        return ASTROZ_OK;
+    }
+    c->cacheValid = false;
     int32_t rc = reserve_time(c, nt);
     if (rc != ASTROZ_OK) return rc;
     const size_t cap = c->dTime.cap / 4;
@@ -443,6 +462,15 @@ int32_t upload_time_axis(Constellation *c, const double *jd, const double *fr, u
         AZ_CUDA(cudaMemcpyAsync(c->dTime.p + k * cap, c->hTime + (size_t)k * nt, (size_t)nt * 8, cudaMemcpyHostToDevice, s));
     AZ_CUDA(cudaEventRecord(c->timeCopied, s));
     c->timePending = true;
+    AZ_CUDA(cudaEventRecord(c->axisReady, s));
+    c->axisStream = s;
+    c->cachedJd.assign(jd, jd + nt);
+    c->cachedFr.assign(fr, fr + nt);
+    c->cachedGmst = (mode != 0);
+    c->cachedRef = c->cat.referenceEpochJd;
+    c->cachedJdMin = lo;
+    c->cachedJdMax = hi;
+    c->cacheValid = true;
     return ASTROZ_OK;
 }
 
@@ -1391,6 +1419,7 @@ int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *
     }
     AZ_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
+    c->cacheValid = false;
     AZ_CUDA(c->dTime.reserve((size_t)count * 2));
     AZ_CUDA(c->dPos.reserve((size_t)count * 6));
     AZ_CUDA(cudaMemcpyAsync(c->dTime.p, jd, (size_t)count * 8, cudaMemcpyHostToDevice, st));

@@ -826,12 +826,14 @@ cudaError_t launch_sgp4_grid_f32(const GridArgs &a, int phase64, cudaStream_t st
 // ---------------------------------------------------------------------------------------------------
 // fp64 roofline denominator.  Two figures:
 //   * the pipe's arithmetic peak: SMs x 64 DFMA lanes x 2 FLOP x the maximum SM clock;
-//   * a live DFMA microbenchmark: 8 independent chains per thread, each x = fma(x, a, b) with a, b in the constant bank
-//     (one register source per instruction -- the pattern tools/fp64_probe.cu measured at the pipe's full rate), run
-//     long enough for the clocks to settle (~0.2 s of warm-up), best of 10.
+//   * a live DFMA microbenchmark: 8 independent chains per thread, each x = fma(x, a, 0.5) -- the multiplier sits in one
+//     register every instruction re-reads from the operand-reuse cache and the addend is an immediate, so the register
+//     file serves one fresh 64-bit pair per DFMA (the pattern tools/fp64_probe.cu measured at the pipe's full rate;
+//     fma(x, ra, rb) with two live register operands reads 8 % lower), run long enough for the clocks to settle
+//     (~0.2 s of warm-up), best of 10.
 // bench.py reports the roofline against the larger of the two.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a, double b) {
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double a) {
     double x[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) x[k] = threadIdx.x * 1e-9 + k;
@@ -840,7 +842,7 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) x[k] = fma(x[k], a, b);
+            for (int k = 0; k < 8; ++k) x[k] = fma(x[k], a, 0.5);  // SASS: DFMA R, R, Ra.reuse, 0.5 -- one live register read
         }
     }
     double s = 0.0;
@@ -877,7 +879,7 @@ cudaError_t measure_fp64_peak(double *flops) {
     float best = 1e30f;
     for (int rep = 0; rep < 60; ++rep) {
         cudaEventRecord(e0);
-        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999);
         cudaEventRecord(e1);
         rc = cudaEventSynchronize(e1);
         if (rc != cudaSuccess) break;

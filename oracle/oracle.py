@@ -298,22 +298,32 @@ def simd_lib() -> C.CDLL:
         L.azo_simd_free.argtypes = [C.c_void_p]
         L.azo_simd_propagate.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, dp, C.c_int, C.c_int]
         L.azo_simd_propagate.restype = C.c_int
+        L.azo_simd_propagate2.argtypes = [C.c_void_p, dp, dp, C.c_size_t, dp, dp, C.c_int, C.c_int, C.c_int]
+        L.azo_simd_propagate2.restype = C.c_int
+        L.azo_simd_counts.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        L.azo_simd_counts.restype = None
         L.azo_simd_isa.restype = C.c_char_p
         _simd = L
     return _simd
 
 
 class SimdConstellation:
-    """Near-earth constellation on the CPU SIMD baseline (src/Constellation.zig:101-200,245-308)."""
+    """Mixed SGP4/SDP4 constellation on the CPU SIMD baseline (src/Constellation.zig:101-200,245-476)."""
 
     def __init__(self, tles, grav: int = WGS72):
         a1, a2 = _lines(tles)
         self.n = len(tles)
         self._h = simd_lib().azo_simd_create(a1, a2, self.n, grav)
         if not self._h:
-            raise ValueError("SIMD baseline: init failed (deep-space or invalid element set in the catalog)")
+            raise ValueError("SIMD baseline: init failed (invalid element set in the catalog)")
+        n, ns, nd = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        simd_lib().azo_simd_counts(self._h, C.byref(n), C.byref(ns), C.byref(nd))
+        self.numSgp4, self.numSdp4 = ns.value, nd.value
 
-    def propagate(self, jd, fr, layout: int = 1, velocities: bool = True, threads: int | None = None, out=None):
+    def propagate(self, jd, fr, layout: int = 1, velocities: bool = True, threads: int | None = None, out=None,
+                  sdp4_threads: int = 0):
+        """sdp4_threads = 0: the reference's own rule (the deep-space phase gets only the threads the near-earth
+        phase left over -- one, when that phase used them all, src/Constellation.zig:358-364); > 0: that many."""
         jd = np.ascontiguousarray(jd, dtype=np.float64)
         fr = np.ascontiguousarray(fr, dtype=np.float64)
         nt = len(jd)
@@ -327,8 +337,8 @@ class SimdConstellation:
         env = os.environ.get("ASTROZ_THREADS")
         if env:
             threads = int(env)
-        simd_lib().azo_simd_propagate(self._h, _dp(jd), _dp(fr), nt, _dp(pos), _dp(vel) if vel is not None else None,
-                                      layout, threads)
+        simd_lib().azo_simd_propagate2(self._h, _dp(jd), _dp(fr), nt, _dp(pos), _dp(vel) if vel is not None else None,
+                                       layout, threads, int(sdp4_threads))
         return pos, vel
 
     def __del__(self):
