@@ -94,6 +94,8 @@ def lib() -> C.CDLL:
         "astroz_cuda_sgp4_propagate": (i32, [vp, C.c_double, dp, dp]),
         "astroz_cuda_sgp4_propagate_batch": (i32, [vp, dp, dp, u32]),
         "astroz_cuda_sgp4_array": (i32, [vp, dp, dp, C.c_double, dp, u32]),
+        "astroz_cuda_constellation_devices": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(u32)]),
+        "astroz_cuda_constellation_propagate_replicated": (i32, [vp, dp, dp, u32, i32, C.POINTER(vp), C.POINTER(vp)]),
         "astroz_cuda_fp64_peak": (i32, [i32, dp]),
         "astroz_cuda_fp64_pipe_peak": (i32, [i32, dp]),
     }
@@ -121,7 +123,8 @@ EXPORTS = [
     "astroz_cuda_constellation_coarse_screen_device", "astroz_cuda_sgp4_screen_all", "astroz_cuda_sgp4_init",
     "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch", "astroz_cuda_sgp4_elements",
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",
-    "astroz_cuda_fp64_peak", "astroz_cuda_fp64_pipe_peak",
+    "astroz_cuda_fp64_peak", "astroz_cuda_fp64_pipe_peak", "astroz_cuda_constellation_devices",
+    "astroz_cuda_constellation_propagate_replicated",
 ]
 
 

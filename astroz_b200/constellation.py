@@ -39,7 +39,9 @@ class Constellation:
     ----------
     tles : sequence of (line1, line2)
     grav : WGS72 (1, python default of the reference) or WGS84 (0)
-    device : CUDA device index
+    device : CUDA device index, or -1 for a multi-device handle over every visible GPU (ASTROZ_DEVICES caps the
+             count, like the reference's ASTROZ_THREADS, src/Constellation.zig:61-74): one `propagate` call then
+             runs all GPUs, each copying its satellite range over its own PCIe link into the caller's block.
     """
 
     def __init__(self, tles, grav: int = _lib.WGS72, device: int = 0):
@@ -118,6 +120,29 @@ class Constellation:
         self.numSatellites, self.numSgp4, self.numSdp4 = cn.value, ns.value, nd.value
         self.device, self.grav = int(device), int(grav)
         return self
+
+    @property
+    def devices(self):
+        """(device ordinals, first catalog row of each device's satellite range + [n]) behind this handle."""
+        n = C.c_int32()
+        check(lib().astroz_cuda_constellation_devices(self._h, C.byref(n), None, None))
+        ids = (C.c_int32 * n.value)()
+        rows = (C.c_uint32 * (n.value + 1))()
+        check(lib().astroz_cuda_constellation_devices(self._h, C.byref(n), ids, rows))
+        return list(ids), list(rows)
+
+    def propagate_replicated(self, jd, fr, velocities: bool = True):
+        """The north star's all-gather behind one (multi-device) handle: TEME, satellite-major; the whole
+        (n, n_times, 3) block(s) end up in the HBM of every device of the handle, stored there from inside the
+        propagation kernels over NVLink peer mappings.  Returns (devices, pos_ptrs, vel_ptrs): raw device pointers
+        per device, owned by the handle."""
+        jd, fr = as_f64(jd), as_f64(fr)
+        ids, _ = self.devices
+        pp = (C.c_void_p * len(ids))()
+        pv = (C.c_void_p * len(ids))()
+        check(lib().astroz_cuda_constellation_propagate_replicated(self._h, dptr(jd), dptr(fr), jd.shape[0],
+                                                                    1 if velocities else 0, pp, pv))
+        return ids, [int(p or 0) for p in pp], [int(p or 0) for p in pv]
 
     def deinit(self) -> None:
         """Constellation.deinit (src/Constellation.zig:202-210)."""

@@ -31,6 +31,15 @@ int32_t cuda_fail(cudaError_t e, const char *what) {
         if (_e != cudaSuccess) return cuda_fail(_e, #expr);  \
     } while (0)
 
+#define AZ_SINGLE(c)                                                                                        \
+    do {                                                                                                    \
+        if ((c) && (c)->multi()) {                                                                          \
+            g_lastError = "this entry point works on device pointers of ONE GPU: create the handle with "  \
+                          "device >= 0 (a device = -1 handle spans several GPUs)";                          \
+            return ASTROZ_VALUE_ERROR;                                                                      \
+        }                                                                                                   \
+    } while (0)
+
 int32_t status_to_code(int st) {  // kernel-level code -> C API code (src/c_api/sgp4.zig:22-28)
     switch (st) {
         case az::kOk: return ASTROZ_OK;
@@ -115,13 +124,25 @@ struct Constellation {
     bool timed = false, spanTimed = false;
     int variant = -1;  // -1 = shipped default; >= 0 selects a tuning variant (ASTROZ_SGP4_VARIANT)
     int chunks = 8;
+    // Multi-device handle (device = -1 at creation): the catalog is cut into contiguous satellite ranges, one
+    // single-device shard each (the analogue of the reference's thread fan-out, src/Constellation.zig:327-385, with
+    // ASTROZ_DEVICES in the role of ASTROZ_THREADS, :61-74).  The top-level object then holds only the catalog.
+    std::vector<Constellation *> shards;
+    std::vector<uint32_t> shardRow0;   // first catalog row of each shard, plus the end (size = shards + 1)
+    std::vector<uint32_t> shardNear0;  // first near-earth index of each shard, plus the end
+    std::vector<uint32_t> shardDeep0;  // first deep-space index of each shard, plus the end
+    DevBuf<double> dFullPos, dFullVel; // per shard: the WHOLE block, for the replicated (all-gather) propagate
+    bool multi() const { return !shards.empty(); }
 
     ~Constellation() {
+        for (Constellation *sh : shards) delete sh;
+        shards.clear();
         if (!stream) return;  // never opened on a device (a Satrec that was only inspected): nothing to release
         cudaSetDevice(device);
         dTiles.release(); dToff.release(); dSgp4Orig.release(); dSdp4Orig.release(); dIdentity.release(); dSdp4Identity.release();
         dSdp4.release(); dTime.release(); dToffCall.release(); dMask.release(); dLattice.release(); dPos.release(); dVel.release();
         dHead.release(); dNext.release(); dPairs.release(); dTIdx.release(); dCount.release();
+        dFullPos.release(); dFullVel.release();
         for (auto &h : hTimeSlot) if (h) cudaFreeHost(h);
         if (hToffCall) cudaFreeHost(hToffCall);
         for (auto &e : slotCopied) if (e) cudaEventDestroy(e);
@@ -203,6 +224,75 @@ int32_t finish_create(Constellation *c, int device) {
             c->sdp4EpochMin = std::min(c->sdp4EpochMin, r.epochJd);
             c->sdp4EpochMax = std::max(c->sdp4EpochMax, r.epochJd);
         }
+    }
+    return ASTROZ_OK;
+}
+
+// Devices of a device = -1 handle: ASTROZ_DEVICE_LIST="0,2,3" names ordinals explicitly (an ordinal may repeat: several
+// shards on one GPU, which is how the sharding is exercised on a one-GPU box); otherwise the first ASTROZ_DEVICES of the
+// visible devices (all of them when unset) -- the device-count knob in the role of ASTROZ_THREADS
+// (src/Constellation.zig:61-74).
+std::vector<int> multi_device_list() {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) count = 0;
+    std::vector<int> devs;
+    if (const char *lst = std::getenv("ASTROZ_DEVICE_LIST")) {
+        const char *p = lst;
+        while (*p) {
+            char *end = nullptr;
+            const long v = std::strtol(p, &end, 10);
+            if (end == p) break;
+            if (v >= 0 && v < count) devs.push_back((int)v);
+            p = (*end == ',') ? end + 1 : end;
+        }
+        if (!devs.empty()) return devs;
+    }
+    int want = count;
+    if (const char *v = std::getenv("ASTROZ_DEVICES")) {
+        const int k = std::atoi(v);
+        if (k >= 1) want = std::min(count, k);
+    }
+    for (int d = 0; d < want; ++d) devs.push_back(d);
+    return devs;
+}
+
+// Open the handle on `device` (>= 0), or cut the catalog into one shard per device (device = -1).
+int32_t finish_create_any(Constellation *c, int device) {
+    if (device >= 0) return finish_create(c, device);
+    if (device != -1) {
+        g_lastError = "device must be a CUDA ordinal, or -1 for every visible device (ASTROZ_DEVICES caps the count)";
+        return ASTROZ_VALUE_ERROR;
+    }
+    const std::vector<int> devs = multi_device_list();
+    const az::CatalogTables &t = c->cat;
+    // satellite ranges of equal cost (a deep-space cell costs ~2.4 near-earth cells), cut on multiples of 8 rows so every
+    // shard's rows start 64-byte aligned in either layout
+    size_t want = std::min<size_t>(devs.size(), std::max<uint32_t>(1u, t.n / 64));
+    if (want <= 1) return finish_create(c, devs.empty() ? 0 : devs[0]);
+    std::vector<double> prefix(t.n + 1, 0.0);
+    for (uint32_t i = 0; i < t.n; ++i) prefix[i + 1] = prefix[i] + (t.classes[i] == 0 ? 1.0 : 2.4);
+    std::vector<uint32_t> cut(1, 0u);
+    for (size_t k = 1; k < want; ++k) {
+        const double target = prefix[t.n] * (double)k / (double)want;
+        uint32_t r = (uint32_t)(std::lower_bound(prefix.begin(), prefix.end(), target) - prefix.begin());
+        r = std::min(t.n, (r + 4) / 8 * 8);
+        if (r > cut.back() && r < t.n) cut.push_back(r);
+    }
+    cut.push_back(t.n);
+    c->g = az::grav_consts(t.grav);
+    c->device = devs[0];
+    c->shardRow0 = cut;
+    c->shardNear0.assign(1, 0u);
+    c->shardDeep0.assign(1, 0u);
+    for (size_t k = 0; k + 1 < cut.size(); ++k) {
+        Constellation *sh = new (std::nothrow) Constellation();
+        if (!sh) return ASTROZ_ALLOC_FAILED;
+        c->shards.push_back(sh);
+        az::slice_catalog(t, cut[k], cut[k + 1], sh->cat);
+        c->shardNear0.push_back(c->shardNear0.back() + sh->cat.nSgp4);
+        c->shardDeep0.push_back(c->shardDeep0.back() + sh->cat.nSdp4);
+        const int32_t rc = finish_create(sh, devs[k % devs.size()]);
+        if (rc != ASTROZ_OK) return rc;
     }
     return ASTROZ_OK;
 }
@@ -535,7 +625,7 @@ int32_t astroz_cuda_constellation_create(const char *const *line1, const char *c
         delete c;
         return status_to_code(rc);
     }
-    int32_t e = finish_create(c, device);
+    int32_t e = finish_create_any(c, device);
     if (e != ASTROZ_OK) {
         delete c;
         return e;
@@ -585,7 +675,7 @@ int32_t astroz_cuda_constellation_create_from_elements(const double *epoch_jd, c
         delete c;
         return status_to_code(rc);
     }
-    int32_t e = finish_create(c, device);
+    int32_t e = finish_create_any(c, device);
     if (e != ASTROZ_OK) {
         delete c;
         return e;
@@ -660,9 +750,20 @@ int32_t astroz_cuda_constellation_get_reference_epoch(astroz_constellation_t h, 
 int32_t astroz_cuda_constellation_set_reference_epoch(astroz_constellation_t h, double jd) {
     if (!h) return ASTROZ_NULL_POINTER;
     Constellation *c = static_cast<Constellation *>(h);
+    if (c->multi()) {
+        c->cat.referenceEpochJd = jd;
+        for (Constellation *sh : c->shards) {
+            const int32_t rc = astroz_cuda_constellation_set_reference_epoch(sh, jd);
+            if (rc != ASTROZ_OK) return rc;
+        }
+        return ASTROZ_OK;
+    }
     AZ_CUDA(cudaSetDevice(c->device));
-    AZ_CUDA(cudaStreamSynchronize(c->stream));
+    // kernels still reading the old offsets may sit on the handle's stream or on a caller's stream that was given to a
+    // _device call: the whole device is drained, this is a cold configuration call
+    AZ_CUDA(cudaDeviceSynchronize());
     c->cat.referenceEpochJd = jd;
+    c->cacheValid = false;
     return upload_toff(c);
 }
 
@@ -671,6 +772,7 @@ int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, con
                                                    int32_t mode, int32_t layout, uint32_t out_num_sats,
                                                    uint32_t out_sat_offset, void *stream) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     int32_t rc = check_args(c, jd, fr, d_pos, mode, layout);
     if (rc != ASTROZ_OK) return rc;
     if (n_times == 0 || c->cat.n == 0) return ASTROZ_OK;
@@ -748,6 +850,7 @@ int32_t astroz_cuda_sdp4_propagate_into_device(astroz_constellation_t h, const d
                                                uint32_t n_times, double *d_pos, double *d_vel, int32_t mode,
                                                int32_t layout, uint32_t out_num_sats, uint32_t sat_offset, void *stream) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     int32_t rc = check_args(c, jd, fr, d_pos, mode, layout);
     if (rc != ASTROZ_OK) return rc;
     if (n_times == 0 || c->cat.nSdp4 == 0) return ASTROZ_OK;
@@ -763,6 +866,7 @@ int32_t astroz_cuda_sdp4_propagate_into(astroz_constellation_t h, const double *
                                         double *pos, double *vel, int32_t mode, int32_t layout, uint32_t out_num_sats,
                                         uint32_t sat_offset) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     int32_t rc = check_args(c, jd, fr, pos, mode, layout);
     if (rc != ASTROZ_OK) return rc;
     const uint32_t nd = c->cat.nSdp4;
@@ -797,6 +901,7 @@ int32_t astroz_cuda_constellation_propagate_device_f32(astroz_constellation_t h,
                                                        uint32_t n_times, double *d_pos, double *d_vel, int32_t phase64,
                                                        void *stream) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     if (!c || !jd || !fr || !d_pos || !d_vel) return ASTROZ_NULL_POINTER;
     if (n_times == 0 || c->cat.nSgp4 == 0) return ASTROZ_OK;
     AZ_CUDA(cudaSetDevice(c->device));
@@ -830,6 +935,7 @@ int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, con
                                                    uint32_t n_peers, void *mc_pos, void *mc_vel, uint32_t out_num_sats,
                                                    uint32_t out_sat_offset, void *stream) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     if (!c || !jd || !fr) return ASTROZ_NULL_POINTER;
     if (!mc_pos && (!peer_pos || n_peers == 0)) return ASTROZ_NULL_POINTER;
     if (n_peers > (uint32_t)az::kMaxPeers) {
@@ -867,11 +973,12 @@ int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, con
     return rc;
 }
 
-int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const double *jd, const double *fr,
-                                            uint32_t n_times, double *pos, double *vel, int32_t mode, int32_t layout) {
-    Constellation *c = static_cast<Constellation *>(h);
-    int32_t rc = check_args(c, jd, fr, pos, mode, layout);
-    if (rc != ASTROZ_OK) return rc;
+// Host-buffer propagate, split in two so a multi-device handle can queue every shard before waiting on any:
+// queue = upload the time axis, launch the grid in chunks, start each chunk's device->host copy as soon as its kernels
+// finish; wait = drain the streams.  This handle's rows land at rows [rowOffset, rowOffset + n) of a host block with
+// totalRows rows (its own block when rowOffset = 0, totalRows = n).
+static int32_t propagate_host_queue(Constellation *c, const double *jd, const double *fr, uint32_t n_times, double *pos,
+                                    double *vel, int32_t mode, int32_t layout, uint32_t rowOffset, uint32_t totalRows) {
     const uint32_t n = c->cat.n;
     if (n_times == 0 || n == 0) return ASTROZ_OK;
     AZ_CUDA(cudaSetDevice(c->device));
@@ -881,7 +988,7 @@ int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const doub
     double *dPos = c->dPos.p, *dVel = vel ? c->dVel.p : nullptr;
     cudaStream_t s = c->stream;
     double jdMin, jdMax;
-    rc = upload_time_axis(c, jd, fr, n_times, mode, s, &jdMin, &jdMax);
+    int32_t rc = upload_time_axis(c, jd, fr, n_times, mode, s, &jdMin, &jdMax);
     if (rc != ASTROZ_OK) return rc;
     rc = prepare_deep_space(c, jdMin, jdMax, s);
     if (rc != ASTROZ_OK) return rc;
@@ -895,6 +1002,7 @@ int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const doub
     uint32_t nChunks = (bySat || byTime) ? std::min<uint32_t>((uint32_t)c->chunks, units) : 1;
     if (total * 8 < (8u << 20)) nChunks = 1;
     const uint32_t per = (units + nChunks - 1) / nChunks;
+    AZ_CUDA(cudaEventRecord(c->ev[4], s));  // whole-call span: first kernel of the first chunk ...
     for (uint32_t k = 0; k < nChunks; ++k) {
         const uint32_t u0 = k * per, u1 = std::min(units, u0 + per);
         if (u0 >= u1) break;
@@ -914,18 +1022,68 @@ int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const doub
             off = 0;
             cnt = total;
         }
-        rc = queue_grid(c, L, n_times, dPos, dVel, nullptr, mode, layout, n, 0, s, k == 0);
+        rc = queue_grid(c, L, n_times, dPos, dVel, nullptr, mode, layout, n, 0, s, false);
         if (rc != ASTROZ_OK) return rc;
         AZ_CUDA(cudaEventRecord(c->chunkDone[k], s));
         AZ_CUDA(cudaStreamWaitEvent(c->copyStream, c->chunkDone[k], 0));
-        AZ_CUDA(cudaMemcpyAsync(pos + off, dPos + off, cnt * 8, cudaMemcpyDeviceToHost, c->copyStream));
-        if (vel) AZ_CUDA(cudaMemcpyAsync(vel + off, dVel + off, cnt * 8, cudaMemcpyDeviceToHost, c->copyStream));
+        for (int which = 0; which < (vel ? 2 : 1); ++which) {
+            double *hdst = which ? vel : pos;
+            const double *dsrc = (which ? dVel : dPos) + off;
+            if (layout == 0) {  // this handle's rows are one contiguous run of the (possibly wider) host block
+                AZ_CUDA(cudaMemcpyAsync(hdst + (size_t)rowOffset * n_times * 3 + off, dsrc, cnt * 8,
+                                        cudaMemcpyDeviceToHost, c->copyStream));
+            } else if (totalRows == n) {
+                AZ_CUDA(cudaMemcpyAsync(hdst + off, dsrc, cnt * 8, cudaMemcpyDeviceToHost, c->copyStream));
+            } else {            // time-major into a wider block: n*24 bytes per epoch at a pitch of totalRows*24
+                AZ_CUDA(cudaMemcpy2DAsync(hdst + ((size_t)u0 * totalRows + rowOffset) * 3, (size_t)totalRows * 24, dsrc,
+                                          (size_t)n * 24, (size_t)n * 24, u1 - u0, cudaMemcpyDeviceToHost,
+                                          c->copyStream));
+            }
+        }
     }
+    AZ_CUDA(cudaEventRecord(c->ev[5], s));  // ... to the last kernel of the last chunk
+    // last_kernel_ms after a host-buffer call: ms[1] = the span above (all chunks, copies overlapping); the per-kernel
+    // slots repeat it
+    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    AZ_CUDA(cudaEventRecord(c->ev[3], s));
     c->timed = true;
-    c->spanTimed = false;
-    AZ_CUDA(cudaStreamSynchronize(c->copyStream));
-    AZ_CUDA(cudaStreamSynchronize(s));
+    c->spanTimed = true;
     return ASTROZ_OK;
+}
+
+static int32_t propagate_host_wait(Constellation *c) {
+    if (!c->stream) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    AZ_CUDA(cudaStreamSynchronize(c->copyStream));
+    AZ_CUDA(cudaStreamSynchronize(c->stream));
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const double *jd, const double *fr,
+                                            uint32_t n_times, double *pos, double *vel, int32_t mode, int32_t layout) {
+    Constellation *c = static_cast<Constellation *>(h);
+    int32_t rc = check_args(c, jd, fr, pos, mode, layout);
+    if (rc != ASTROZ_OK) return rc;
+    if (n_times == 0 || c->cat.n == 0) return ASTROZ_OK;
+    if (!c->multi()) {
+        rc = propagate_host_queue(c, jd, fr, n_times, pos, vel, mode, layout, 0, c->cat.n);
+        if (rc != ASTROZ_OK) return rc;
+        return propagate_host_wait(c);
+    }
+    // one call, every device: each shard computes its satellite range and copies it over its own PCIe link into its
+    // slice of the caller's block; no collective is needed for a host-resident result
+    int32_t first = ASTROZ_OK;
+    for (size_t k = 0; k < c->shards.size(); ++k) {
+        rc = propagate_host_queue(c->shards[k], jd, fr, n_times, pos, vel, mode, layout, c->shardRow0[k], c->cat.n);
+        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
+    }
+    for (Constellation *sh : c->shards) {
+        rc = propagate_host_wait(sh);
+        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
+    }
+    return first;
 }
 
 int32_t astroz_cuda_constellation_reset_carry(astroz_constellation_t h) { return h ? ASTROZ_OK : ASTROZ_NULL_POINTER; }
@@ -933,6 +1091,14 @@ int32_t astroz_cuda_constellation_reset_carry(astroz_constellation_t h) { return
 int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h) {
     if (!h) return ASTROZ_NULL_POINTER;
     Constellation *c = static_cast<Constellation *>(h);
+    if (c->multi()) {
+        for (Constellation *sh : c->shards) {
+            const int32_t rc = astroz_cuda_constellation_synchronize(sh);
+            if (rc != ASTROZ_OK) return rc;
+        }
+        return ASTROZ_OK;
+    }
+    if (!c->stream) return ASTROZ_OK;
     AZ_CUDA(cudaSetDevice(c->device));
     AZ_CUDA(cudaStreamSynchronize(c->stream));
     AZ_CUDA(cudaStreamSynchronize(c->copyStream));
@@ -943,6 +1109,15 @@ int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float
     if (!h || !ms) return ASTROZ_NULL_POINTER;
     Constellation *c = static_cast<Constellation *>(h);
     ms[0] = ms[1] = ms[2] = 0.f;
+    if (c->multi()) {  // the devices run side by side: the slowest one is the call's kernel time
+        for (Constellation *sh : c->shards) {
+            float one[3];
+            const int32_t rc = astroz_cuda_constellation_last_kernel_ms(sh, one);
+            if (rc != ASTROZ_OK) return rc;
+            for (int k = 0; k < 3; ++k) ms[k] = std::max(ms[k], one[k]);
+        }
+        return ASTROZ_OK;
+    }
     if (!c->timed) return ASTROZ_NOT_INITIALIZED;
     AZ_CUDA(cudaSetDevice(c->device));
     AZ_CUDA(cudaEventSynchronize(c->ev[1]));
@@ -1033,6 +1208,7 @@ int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const d
                                                double reference_jd, int32_t layout, const uint8_t *satellite_mask,
                                                uint32_t out_num_sats, void *stream) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     int32_t rc = check_args(c, times, epoch_offsets, d_pos, mode, layout);
     if (rc != ASTROZ_OK) return rc;
     if (n_times == 0 || c->cat.nSgp4 == 0) return ASTROZ_OK;
@@ -1044,6 +1220,47 @@ int32_t astroz_cuda_sgp4_propagate_into_device(astroz_constellation_t h, const d
     cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : c->stream;
     return sgp4_into_common(c, times, n_times, epoch_offsets, d_pos, d_vel, mode, reference_jd, layout, s, 3,
                             satellite_mask, out_num_sats);
+}
+
+// Host-buffer form of the stateless near-earth path, in queue / wait halves like propagate_host_queue.  Near-earth
+// satellite i of this handle lands in row rowOffset + i of a host block with `rows` rows; epoch_offsets / mask are
+// already offset to this handle's first satellite.
+static int32_t sgp4_into_host_queue(Constellation *c, const double *times, uint32_t n_times, const double *epoch_offsets,
+                                    double *pos, double *vel, int32_t mode, double reference_jd, int32_t layout,
+                                    const uint8_t *mask, uint32_t rows, uint32_t rowOffset) {
+    const uint32_t ns = c->cat.nSgp4;
+    if (n_times == 0 || ns == 0) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    // the near-earth rows are computed as a dense (ns, n_times) block on the device and placed in the caller's
+    // (possibly wider) block with one strided copy per array; rows that belong to other satellites are never touched
+    const size_t dense = (size_t)ns * n_times * 3;
+    AZ_CUDA(c->dPos.reserve(dense));
+    if (vel) AZ_CUDA(c->dVel.reserve(dense));
+    const bool strided = (layout == 1 && rows != ns);
+    auto host_at = [&](double *base) {
+        return base + (layout == 0 ? (size_t)rowOffset * n_times * 3 : (size_t)rowOffset * 3);
+    };
+    if (mask) {  // masked rows must keep the caller's contents: stage the caller's rows, overwrite the active ones
+        for (int which = 0; which < (vel ? 2 : 1); ++which) {
+            double *dst = which ? c->dVel.p : c->dPos.p;
+            const double *src = host_at(which ? vel : pos);
+            if (!strided) AZ_CUDA(cudaMemcpyAsync(dst, src, dense * 8, cudaMemcpyHostToDevice, s));
+            else AZ_CUDA(cudaMemcpy2DAsync(dst, (size_t)ns * 24, src, (size_t)rows * 24, (size_t)ns * 24, n_times,
+                                           cudaMemcpyHostToDevice, s));
+        }
+    }
+    int32_t rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode,
+                                  reference_jd, layout, s, 3, mask, ns);
+    if (rc != ASTROZ_OK) return rc;
+    for (int which = 0; which < (vel ? 2 : 1); ++which) {
+        double *dst = host_at(which ? vel : pos);
+        const double *src = which ? c->dVel.p : c->dPos.p;
+        if (!strided) AZ_CUDA(cudaMemcpyAsync(dst, src, dense * 8, cudaMemcpyDeviceToHost, s));
+        else AZ_CUDA(cudaMemcpy2DAsync(dst, (size_t)rows * 24, src, (size_t)ns * 24, (size_t)ns * 24, n_times,
+                                       cudaMemcpyDeviceToHost, s));
+    }
+    return ASTROZ_OK;
 }
 
 int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *times, uint32_t n_times,
@@ -1060,42 +1277,25 @@ int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *
         g_lastError = "out_num_sats smaller than the number of near-earth satellites";
         return ASTROZ_VALUE_ERROR;
     }
-    AZ_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = c->stream;
-    if (!satellite_mask) {
-        // every near-earth row is written: compute them as a dense block and place it in the caller's (possibly
-        // wider) block with one strided copy; rows that belong to other satellites are never touched
-        const size_t dense = (size_t)ns * n_times * 3;
-        AZ_CUDA(c->dPos.reserve(dense));
-        if (vel) AZ_CUDA(c->dVel.reserve(dense));
-        rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode, reference_jd,
-                              layout, s, 3, nullptr, ns);
+    if (!c->multi()) {
+        rc = sgp4_into_host_queue(c, times, n_times, epoch_offsets, pos, vel, mode, reference_jd, layout, satellite_mask,
+                                  rows, 0);
         if (rc != ASTROZ_OK) return rc;
-        for (int which = 0; which < (vel ? 2 : 1); ++which) {
-            double *dst = which ? vel : pos;
-            const double *src = which ? c->dVel.p : c->dPos.p;
-            if (layout == 0 || rows == ns)
-                AZ_CUDA(cudaMemcpyAsync(dst, src, dense * 8, cudaMemcpyDeviceToHost, s));
-            else
-                AZ_CUDA(cudaMemcpy2DAsync(dst, (size_t)rows * 24, src, (size_t)ns * 24, (size_t)ns * 24, n_times,
-                                          cudaMemcpyDeviceToHost, s));
-        }
-        AZ_CUDA(cudaStreamSynchronize(s));
+        AZ_CUDA(cudaStreamSynchronize(c->stream));
         return ASTROZ_OK;
     }
-    // masked rows must keep the caller's contents: stage the caller's block, overwrite the active rows, copy back
-    const size_t total = (size_t)rows * n_times * 3;
-    AZ_CUDA(c->dPos.reserve(total));
-    if (vel) AZ_CUDA(c->dVel.reserve(total));
-    AZ_CUDA(cudaMemcpyAsync(c->dPos.p, pos, total * 8, cudaMemcpyHostToDevice, s));
-    if (vel) AZ_CUDA(cudaMemcpyAsync(c->dVel.p, vel, total * 8, cudaMemcpyHostToDevice, s));
-    rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode, reference_jd,
-                          layout, s, 3, satellite_mask, rows);
-    if (rc != ASTROZ_OK) return rc;
-    AZ_CUDA(cudaMemcpyAsync(pos, c->dPos.p, total * 8, cudaMemcpyDeviceToHost, s));
-    if (vel) AZ_CUDA(cudaMemcpyAsync(vel, c->dVel.p, total * 8, cudaMemcpyDeviceToHost, s));
-    AZ_CUDA(cudaStreamSynchronize(s));
-    return ASTROZ_OK;
+    int32_t first = ASTROZ_OK;
+    for (size_t k = 0; k < c->shards.size(); ++k) {
+        const uint32_t near0 = c->shardNear0[k];
+        rc = sgp4_into_host_queue(c->shards[k], times, n_times, epoch_offsets + near0, pos, vel, mode, reference_jd, layout,
+                                  satellite_mask ? satellite_mask + near0 : nullptr, rows, near0);
+        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
+    }
+    for (Constellation *sh : c->shards) {
+        rc = propagate_host_wait(sh);
+        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
+    }
+    return first;
 }
 
 int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, uint32_t n_times,
@@ -1103,6 +1303,7 @@ int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, u
                                 double reference_jd, double *out_min_dists, uint32_t *out_min_t) {
     (void)reference_jd;
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     if (!c || !times || !epoch_offsets || !out_min_dists || !out_min_t) return ASTROZ_NULL_POINTER;
     const uint32_t ns = c->cat.nSgp4;
     if (ns == 0 || n_times == 0) return ASTROZ_OK;
@@ -1202,6 +1403,7 @@ int32_t astroz_cuda_constellation_coarse_screen_device(astroz_constellation_t h,
                                                        double threshold, const uint8_t *d_valid_mask, uint32_t *d_pairs,
                                                        uint32_t *d_t_indices, uint32_t max_results, uint64_t *count) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     if (!c || !d_positions || !count || (max_results && (!d_pairs || !d_t_indices))) return ASTROZ_NULL_POINTER;
     if (layout < 0 || layout > 1 || !(threshold > 0.0)) {
         g_lastError = "coarse screen: layout must be 0/1 and threshold positive";
@@ -1218,6 +1420,7 @@ int32_t astroz_cuda_sgp4_screen_all(astroz_constellation_t h, const double *time
                                     const double *epoch_offsets, double threshold, uint32_t *pairs, uint32_t *t_indices,
                                     uint32_t max_results, uint64_t *count) {
     Constellation *c = static_cast<Constellation *>(h);
+    AZ_SINGLE(c);
     if (!c || !times || !epoch_offsets || !count || (max_results && (!pairs || !t_indices))) return ASTROZ_NULL_POINTER;
     if (!(threshold > 0.0)) return ASTROZ_VALUE_ERROR;
     *count = 0;
@@ -1458,6 +1661,102 @@ int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3]
     std::memcpy(pos, r, 24);
     std::memcpy(vel, r + 3, 24);
     return rc;
+}
+
+// ---- multi-device handles --------------------------------------------------------------------------------
+int32_t astroz_cuda_constellation_devices(astroz_constellation_t h, int32_t *n_devices, int32_t *device_ids,
+                                          uint32_t *first_rows) {
+    if (!h || !n_devices) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    if (!c->multi()) {
+        *n_devices = 1;
+        if (device_ids) device_ids[0] = c->device;
+        if (first_rows) { first_rows[0] = 0; first_rows[1] = c->cat.n; }
+        return ASTROZ_OK;
+    }
+    *n_devices = (int32_t)c->shards.size();
+    for (size_t k = 0; k < c->shards.size(); ++k) {
+        if (device_ids) device_ids[k] = c->shards[k]->device;
+        if (first_rows) first_rows[k] = c->shardRow0[k];
+    }
+    if (first_rows) first_rows[c->shards.size()] = c->cat.n;
+    return ASTROZ_OK;
+}
+
+// Peer mappings between every pair of distinct devices of the handle (cudaMalloc memory of one is then directly
+// addressable from kernels on the other: NVLink 5 loads/stores).  Idempotent.
+static int32_t enable_peers(Constellation *c) {
+    for (Constellation *a : c->shards)
+        for (Constellation *b : c->shards) {
+            if (a->device == b->device) continue;
+            int can = 0;
+            AZ_CUDA(cudaDeviceCanAccessPeer(&can, a->device, b->device));
+            if (!can) {
+                g_lastError = "devices " + std::to_string(a->device) + " and " + std::to_string(b->device) +
+                              " have no peer access (no NVLink / P2P path)";
+                return ASTROZ_CUDA_ERROR;
+            }
+            AZ_CUDA(cudaSetDevice(a->device));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess");
+        }
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_propagate_replicated(astroz_constellation_t h, const double *jd, const double *fr,
+                                                       uint32_t n_times, int32_t velocities, double **d_pos,
+                                                       double **d_vel) {
+    Constellation *c = static_cast<Constellation *>(h);
+    if (!c || !jd || !fr || !d_pos || (velocities && !d_vel)) return ASTROZ_NULL_POINTER;
+    const uint32_t n = c->cat.n;
+    const size_t total = (size_t)n * n_times * 3;
+    if (!c->multi()) {  // one device: the block is simply left in HBM
+        if (n_times == 0 || n == 0) return ASTROZ_OK;
+        AZ_CUDA(cudaSetDevice(c->device));
+        AZ_CUDA(c->dFullPos.reserve(total));
+        if (velocities) AZ_CUDA(c->dFullVel.reserve(total));
+        int32_t rc = astroz_cuda_constellation_propagate_device(c, jd, fr, n_times, c->dFullPos.p,
+                                                                velocities ? c->dFullVel.p : nullptr, nullptr,
+                                                                ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR, n, 0, nullptr);
+        if (rc != ASTROZ_OK) return rc;
+        AZ_CUDA(cudaStreamSynchronize(c->stream));
+        d_pos[0] = c->dFullPos.p;
+        if (velocities) d_vel[0] = c->dFullVel.p;
+        return ASTROZ_OK;
+    }
+    if (n_times == 0 || n == 0) return ASTROZ_OK;
+    int32_t rc = enable_peers(c);
+    if (rc != ASTROZ_OK) return rc;
+    const size_t ns = c->shards.size();
+    if (ns > (size_t)az::kMaxPeers) {
+        g_lastError = "at most 8 devices (one NVSwitch domain)";
+        return ASTROZ_VALUE_ERROR;
+    }
+    for (Constellation *sh : c->shards) {  // every device holds the whole block
+        AZ_CUDA(cudaSetDevice(sh->device));
+        AZ_CUDA(sh->dFullPos.reserve(total));
+        if (velocities) AZ_CUDA(sh->dFullVel.reserve(total));
+    }
+    void *pp[az::kMaxPeers] = {}, *pv[az::kMaxPeers] = {};
+    for (size_t k = 0; k < ns; ++k) {
+        pp[k] = c->shards[k]->dFullPos.p;
+        pv[k] = velocities ? c->shards[k]->dFullVel.p : nullptr;
+    }
+    // one fused launch per device: its rows are stored, run by run, into every device's copy of the block
+    int32_t first = ASTROZ_OK;
+    for (size_t k = 0; k < ns; ++k) {
+        rc = astroz_cuda_constellation_propagate_gather(c->shards[k], jd, fr, n_times, pp, velocities ? pv : nullptr,
+                                                        (uint32_t)ns, nullptr, nullptr, n, c->shardRow0[k], nullptr);
+        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
+    }
+    for (size_t k = 0; k < ns; ++k) {  // all stores have landed once every device's stream has drained
+        rc = propagate_host_wait(c->shards[k]);
+        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
+        d_pos[k] = c->shards[k]->dFullPos.p;
+        if (velocities) d_vel[k] = c->shards[k]->dFullVel.p;
+    }
+    return first;
 }
 
 int32_t astroz_cuda_fp64_peak(int32_t device, double *tflops) {

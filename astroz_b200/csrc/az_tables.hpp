@@ -183,6 +183,42 @@ inline int build_catalog_records(const TleRecord *recs, uint32_t n, int gravSel,
     return kOk;
 }
 
+// Rows [r0, r1) of a classified catalog as a catalog of their own (one shard of a multi-device handle): the same
+// element values, output rows renumbered from 0, and the WHOLE catalog's reference epoch, so tsince -- and with it
+// every result bit -- is what the unsharded catalog computes.
+inline void slice_catalog(const CatalogTables &full, uint32_t r0, uint32_t r1, CatalogTables &out) {
+    out = CatalogTables{};
+    out.n = r1 - r0;
+    out.grav = full.grav;
+    out.referenceEpochJd = full.referenceEpochJd;
+    out.epochs.assign(full.epochs.begin() + r0, full.epochs.begin() + r1);
+    out.classes.assign(full.classes.begin() + r0, full.classes.begin() + r1);
+    // both index lists are ascending (catalog order), so a row range is an index range of each
+    const uint32_t *so = full.sgp4Orig.data();
+    const uint32_t a = (uint32_t)(std::lower_bound(so, so + full.nSgp4, r0) - so);
+    const uint32_t b = (uint32_t)(std::lower_bound(so, so + full.nSgp4, r1) - so);
+    const uint32_t *dorig = full.sdp4Orig.data();
+    const uint32_t da = (uint32_t)(std::lower_bound(dorig, dorig + full.nSdp4, r0) - dorig);
+    const uint32_t db = (uint32_t)(std::lower_bound(dorig, dorig + full.nSdp4, r1) - dorig);
+    out.nSgp4 = b - a;
+    out.nSdp4 = db - da;
+    out.sdp4.assign(full.sdp4.begin() + da, full.sdp4.begin() + db);
+    out.sdp4Orig.resize(out.nSdp4);
+    for (uint32_t i = 0; i < out.nSdp4; ++i) out.sdp4Orig[i] = full.sdp4Orig[da + i] - r0;
+    const uint32_t tiles = out.sgp4Tiles_count();
+    out.sgp4Tiles.assign((size_t)tiles * kSgp4TileDoubles, 0.0);
+    out.sgp4Epoch.resize((size_t)tiles * kTileSats);
+    out.sgp4Orig.resize((size_t)tiles * kTileSats);
+    for (uint32_t s = 0; s < tiles * kTileSats; ++s) {
+        const uint32_t src = a + (s < out.nSgp4 ? s : out.nSgp4 - 1);  // padding repeats the last real satellite
+        const double *from = full.sgp4Tiles.data() + (size_t)(src / kTileSats) * kSgp4TileDoubles + (src % kTileSats);
+        double *to = out.sgp4Tiles.data() + (size_t)(s / kTileSats) * kSgp4TileDoubles + (s % kTileSats);
+        for (int c = 0; c < kSgp4Cols; ++c) to[c * kTileSats] = from[c * kTileSats];
+        out.sgp4Epoch[s] = full.sgp4Epoch[src];
+        out.sgp4Orig[s] = full.sgp4Orig[src] - r0;
+    }
+}
+
 // From TLE text lines (src/Tle.zig:49-101).
 inline int build_catalog(const char *const *l1, const char *const *l2, uint32_t n, int gravSel, CatalogTables &out) {
     std::vector<TleRecord> recs(n);

@@ -9,6 +9,16 @@
  * Threading / ownership (same contract as the reference, src/c_api/allocator.zig:9-18 and
  * src/Constellation.zig:88,294): handles are not thread-safe; caller owns every I/O buffer and the
  * library never retains it; device memory is owned by the handle and released by the matching *_free.
+ * A handle keeps ONE copy of its per-call device scratch (time axis, epoch offsets, mask): calls on a handle
+ * must be issued on one stream, or the caller synchronises between calls that use different streams.
+ *
+ * Failed cells.  Deep-space cells are checked like the reference's scalar path (src/Sdp4.zig:913-967: mean
+ * motion <= 0, eccentricity >= 1 or < -0.001, semi-major axis < 0.95, radius < 1 earth radius) and a failing
+ * cell is zero-filled, per satellite (the reference's batch path zero-fills the 8 satellites of the batch,
+ * src/Constellation.zig:468-471,511-528, and applies only the first three checks, src/Sdp4Batch.zig:293-324).
+ * Near-earth cells are never zero-filled -- the reference's near-earth batch path has no reachable failure
+ * (src/Sgp4Batch.zig:147-150) -- the state is stored and the optional status byte reports radius < 1 earth
+ * radius as ASTROZ_CELL_DECAYED (the scalar path's check, src/Sgp4.zig:588-590) as a diagnostic.
  */
 #ifndef ASTROZ_B200_H
 #define ASTROZ_B200_H
@@ -72,6 +82,14 @@ void astroz_cuda_host_free(void *p);
 
 /* Parse n TLEs (NUL-terminated 69-column lines, src/Tle.zig:49-101), classify each as SGP4 or SDP4
  * exactly as src/Constellation.zig:115-126, build the device element tables on `device`.
+ * device = -1: a MULTI-DEVICE handle -- the catalog is cut into contiguous, 8-row-aligned satellite ranges of
+ * equal cost, one per visible GPU (the analogue of the reference's thread fan-out over one propagate call,
+ * src/Constellation.zig:327-385).  The environment variable ASTROZ_DEVICES caps the number of GPUs used, the way
+ * ASTROZ_THREADS caps the reference's threads (src/Constellation.zig:61-74); ASTROZ_DEVICE_LIST="0,2,3" names
+ * ordinals explicitly.  The host-buffer calls (astroz_cuda_constellation_propagate, astroz_cuda_sgp4_propagate_into)
+ * then run every GPU at once, each copying its rows over its own PCIe link into its slice of the caller's block;
+ * results are bit-identical to a single-device handle.  Entry points that take DEVICE pointers need a
+ * single-device handle and return ASTROZ_VALUE_ERROR otherwise.  (The three host constructors accept -1.)
  * Errors: BAD_TLE_LENGTH, INVALID_ECC, DECAYED (first offending TLE aborts, as the reference). */
 int32_t astroz_cuda_constellation_create(const char *const *line1, const char *const *line2, uint32_t n,
                                          int32_t grav, int32_t device, astroz_constellation_t *out);
@@ -142,6 +160,22 @@ int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, con
                                                    uint32_t n_times, void *const *peer_pos, void *const *peer_vel,
                                                    uint32_t n_peers, void *mc_pos, void *mc_vel,
                                                    uint32_t out_num_sats, uint32_t out_sat_offset, void *stream);
+
+/* Devices behind a handle: *n_devices (1 for a single-device handle); device_ids[n_devices] (nullable) their CUDA
+ * ordinals; first_rows[n_devices + 1] (nullable) the first catalog row of each device's satellite range, then n. */
+int32_t astroz_cuda_constellation_devices(astroz_constellation_t h, int32_t *n_devices, int32_t *device_ids,
+                                          uint32_t *first_rows);
+
+/* The north star's all-gather behind one handle, without an external communicator: propagate (TEME,
+ * satellite-major) and leave the WHOLE (n, n_times, 3) position block -- and velocity block when velocities != 0 --
+ * in the HBM of EVERY device of a multi-device handle.  Each device's propagation kernels store their rows, run by
+ * run, straight into all devices' copies over NVLink (peer mappings from cudaDeviceEnablePeerAccess), so the
+ * transfer overlaps the fp64 work; the call returns when every copy is complete.  d_pos[k] / d_vel[k] receive the
+ * block pointers on device k (owned by the handle, valid until the next call or free); arrays of n_devices entries.
+ * On a single-device handle the block is simply left on that device. */
+int32_t astroz_cuda_constellation_propagate_replicated(astroz_constellation_t h, const double *jd, const double *fr,
+                                                       uint32_t n_times, int32_t velocities, double **d_pos,
+                                                       double **d_vel);
 
 /* Constellation.resetCarry (src/Constellation.zig:214-218).  The device path re-derives the SDP4
  * resonance state from a 720-minute lattice on every call, so this is a semantic no-op kept for drop-in use. */
@@ -216,7 +250,10 @@ int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h);
 
 /* device time (ms, CUDA events on the launching stream) of the propagation kernels of the last
  * propagate call on this handle: [0] SGP4 grid kernel, [1] span of all grid launches of the call (the two grids of a
- * mixed catalog run side by side on two streams, so [1] < [0] + [2] there), [2] SDP4 grid kernel */
+ * mixed catalog run side by side on two streams, so [1] < [0] + [2] there), [2] SDP4 grid kernel.
+ * After a HOST-buffer call (whose grid is launched in chunks so copies overlap compute) all three slots hold the span
+ * from the first kernel of the first chunk to the last kernel of the last chunk; on a multi-device handle, the
+ * maximum over its devices. */
 int32_t astroz_cuda_constellation_last_kernel_ms(astroz_constellation_t h, float ms[3]);
 
 /* ------------------------------------------------------------------------------------------------

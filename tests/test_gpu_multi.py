@@ -33,3 +33,36 @@ def test_sharded_gather_bitwise(case):
     assert res["nccl_equal"] and res["fused_peer_equal"]
     if res.get("multicast"):
         assert res["fused_multicast_equal"]
+
+
+def test_one_handle_over_all_gpus_matches_one_gpu():
+    """device = -1 on a multi-GPU box: one propagate call, every GPU, each device copying its rows over its own PCIe
+    link; and the replicated (all-gather) propagate over NVLink peer mappings.  Bit for bit the one-GPU result."""
+    n = _ngpu()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import numpy as np
+
+    import astroz_b200 as az
+    from astroz_b200 import synth
+    from tests.test_gpu_parity import _device_block
+
+    tles = synth.mixed_catalog(4001, n_geo=200, n_molniya=60, n_gps=60)
+    jd, fr = synth.time_grid(480)
+    single = az.Constellation(tles, device=0)
+    multi = az.Constellation(tles, device=-1)
+    ids, rows = multi.devices
+    assert ids == list(range(min(n, 8))) and rows[-1] == 4001
+    for layout in (0, 1):
+        ps, vs = single.propagate(jd, fr, layout=layout)
+        pm, vm = multi.propagate(jd, fr, layout=layout)
+        assert np.array_equal(ps, pm) and np.array_equal(vs, vm)
+    ps, vs = single.propagate(jd, fr, layout=0)
+    ids, ppos, pvel = multi.propagate_replicated(jd, fr)
+    from cuda import cudart
+
+    for k, d in enumerate(ids):
+        cudart.cudaSetDevice(d)
+        assert np.array_equal(_device_block(ppos[k], ps.shape), ps)
+        assert np.array_equal(_device_block(pvel[k], vs.shape), vs)
+    cudart.cudaSetDevice(0)

@@ -890,3 +890,100 @@ def test_many_satrec_objects_are_cheap_until_propagated(az, oracle, synth):
     for k in (0, 1234, 2999):     # a lazily opened handle gives the same numbers as the batch
         e1, r1, v1 = sats[k].sgp4(jd[5], fr[5])
         assert e1 == 0 and _maxerr(np.array(r1), r[k, 5]) < 1e-9 and _maxerr(np.array(v1), v[k, 5]) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------- multi-device handle
+def _device_block(ptr, shape):
+    """Copy a raw device block (a pointer the library owns) to the host."""
+    from cuda import cudart
+
+    out = np.empty(shape)
+    (err,) = cudart.cudaMemcpy(out.ctypes.data, ptr, out.nbytes, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost)
+    assert int(err) == 0, err
+    return out
+
+
+def test_multi_device_handle_shards_are_bit_identical(az, oracle, synth, monkeypatch):
+    """device = -1: ONE handle whose propagate call fans out over the devices (src/Constellation.zig:327-385 fans out
+    over threads).  On a one-GPU box ASTROZ_DEVICE_LIST repeats the ordinal, so the sharding, the per-shard row
+    offsets and strided copies, and the shared reference epoch are exercised all the same: every result must equal
+    the single-device handle's bit for bit."""
+    tles = synth.mixed_catalog(1003, n_geo=90, n_molniya=40, n_gps=30)
+    jd, fr = synth.time_grid(1440)
+    jd, fr = jd[::7].copy(), fr[::7].copy()
+    single = az.Constellation(tles, device=0)
+    monkeypatch.setenv("ASTROZ_DEVICE_LIST", "0,0,0")
+    multi = az.Constellation(tles, device=-1)
+    monkeypatch.delenv("ASTROZ_DEVICE_LIST")
+    ids, rows = multi.devices
+    assert ids == [0, 0, 0] and rows[0] == 0 and rows[-1] == 1003 and all(r % 8 == 0 for r in rows[:-1])
+    assert all(250 < rows[k + 1] - rows[k] < 420 for k in range(3))   # equal-cost ranges (deep-space rows weigh 2.4)
+    assert (multi.numSatellites, multi.numSgp4, multi.numSdp4) == (single.numSatellites, single.numSgp4, single.numSdp4)
+    assert np.array_equal(multi.classes, single.classes) and np.array_equal(multi.epochs, single.epochs)
+    assert multi.referenceEpochJd == single.referenceEpochJd
+    for layout in (az.Layout.satelliteMajor, az.Layout.timeMajor):
+        for mode in (az.OutputMode.teme, az.OutputMode.ecef, az.OutputMode.geodetic):
+            for velocities in (True, False):
+                ps, vs = single.propagate(jd, fr, outputMode=mode, layout=layout, velocities=velocities)
+                pm, vm = multi.propagate(jd, fr, outputMode=mode, layout=layout, velocities=velocities)
+                assert np.array_equal(ps, pm), (layout, mode, velocities)
+                assert (vs is None and vm is None) or np.array_equal(vs, vm)
+    # caller-owned pageable buffers take the same route
+    pp, vp = np.zeros((1003, len(jd), 3)), np.zeros((1003, len(jd), 3))
+    multi.propagate(jd, fr, pp, vp, layout=az.Layout.satelliteMajor)
+    ps, vs = single.propagate(jd, fr, layout=az.Layout.satelliteMajor)
+    assert np.array_equal(pp, ps) and np.array_equal(vp, vs)
+    po, vo, _, _ = oracle.constellation_propagate(tles, jd, fr, threads=0)
+    assert _maxerr(pp, po) < POS_TOL and _maxerr(vp, vo) < VEL_TOL
+    # the stateless near-earth path, with a mask and a wider block
+    ns = single.numSgp4
+    times = np.arange(0.0, 300.0, 3.0)
+    off = (2460437.5 - single.epochs[np.asarray(single.classes) == 0]) * 1440.0
+    mask = np.ones(ns, dtype=np.uint8)
+    mask[::5] = 0
+    for tm in (False, True):
+        shape = (ns + 9, len(times), 3) if not tm else (len(times), ns + 9, 3)
+        a_p, a_v, b_p, b_v = (np.full(shape, 3.0) for _ in range(4))
+        single.propagate_into(times, a_p, a_v, epoch_offsets=off, satellite_mask=mask, time_major=tm, output_stride=ns + 9)
+        multi.propagate_into(times, b_p, b_v, epoch_offsets=off, satellite_mask=mask, time_major=tm, output_stride=ns + 9)
+        assert np.array_equal(a_p, b_p) and np.array_equal(a_v, b_v)
+    # a shared reference epoch can be moved, and every shard follows
+    multi.referenceEpochJd = single.referenceEpochJd + 0.25
+    single.referenceEpochJd = single.referenceEpochJd + 0.25
+    assert np.array_equal(multi.propagate(jd, fr, layout=0)[0], single.propagate(jd, fr, layout=0)[0])
+    # device-pointer entry points need one device
+    import torch
+
+    t = torch.empty((1003, len(jd), 3), dtype=torch.float64, device="cuda")
+    with pytest.raises(az.AstrozCudaError) as ei:
+        multi.propagate_device(jd, fr, t)
+    assert ei.value.code == -20
+    # the all-gather behind one handle: every device of the handle ends with the whole block
+    single.referenceEpochJd = single.referenceEpochJd - 0.25
+    multi.referenceEpochJd = multi.referenceEpochJd - 0.25
+    ids, ppos, pvel = multi.propagate_replicated(jd, fr)
+    ps, vs = single.propagate(jd, fr, layout=0)
+    for k in range(len(ids)):
+        assert np.array_equal(_device_block(ppos[k], ps.shape), ps)
+        assert np.array_equal(_device_block(pvel[k], vs.shape), vs)
+    ids1, p1, v1 = single.propagate_replicated(jd, fr, velocities=False)
+    assert ids1 == [0] and v1 == [0] and np.array_equal(_device_block(p1[0], ps.shape), ps)
+
+
+def test_multi_device_handle_device_count_knob(az, synth, monkeypatch):
+    """ASTROZ_DEVICES caps the GPUs of a device = -1 handle the way ASTROZ_THREADS caps the reference's threads
+    (src/Constellation.zig:61-74); with one device left the handle is an ordinary single-device one."""
+    import torch
+
+    tles = synth.near_earth_catalog(512)
+    monkeypatch.setenv("ASTROZ_DEVICES", "1")
+    c = az.Constellation(tles, device=-1)
+    assert c.devices == ([0], [0, 512])
+    monkeypatch.delenv("ASTROZ_DEVICES")
+    c2 = az.Constellation(tles, device=-1)
+    ids, rows = c2.devices
+    assert len(ids) == min(torch.cuda.device_count(), 8) and rows[-1] == 512
+    jd, fr = synth.time_grid(64)
+    assert np.array_equal(c.propagate(jd, fr)[0], c2.propagate(jd, fr)[0])
+    with pytest.raises(az.AstrozCudaError):
+        az.Constellation(tles, device=-2)
