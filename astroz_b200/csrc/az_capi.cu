@@ -194,6 +194,7 @@ int32_t open_device(Constellation *c, int device) {
     for (auto &ev : c->chunkDone) AZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *v = std::getenv("ASTROZ_SGP4_VARIANT")) c->variant = std::atoi(v);
     if (const char *v = std::getenv("ASTROZ_SDP4_VARIANT")) az::set_sdp4_variant(std::atoi(v));
+    if (const char *v = std::getenv("ASTROZ_K1_STRIPE")) az::set_sgp4_stripe((uint32_t)std::max(0, std::atoi(v)));
     if (const char *v = std::getenv("ASTROZ_D2H_CHUNKS")) c->chunks = std::max(1, std::min(64, std::atoi(v)));
     return ASTROZ_OK;
 }

@@ -290,6 +290,18 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
     kepler_posvel<kN>(am, em, mm, argpm, nodem, sa, g, o);
 }
 
+// Angle of the unit vector (s, c) = (sin a, cos a), a in (-pi, pi]: the fp32 arctangent (idle FMA/XU pipes) is the
+// seed, exactly representable in fp64; one first-order correction with the fp64 sincos of the seed finishes it:
+// d = sin(a - a0) = s cos a0 - c sin a0, |d| < 1e-6, asin(d) - d < 2e-19.  22 fp64 instructions against ~54 for
+// libdevice's atan2 (and no constants to materialise).  The sign of a zero s survives the conversion, so the branch
+// cut at +-pi falls where atan2 puts it.
+AZ_HD double angle_of_unit(double s, double c) {
+    const double a0 = (double)atan2f((float)s, (float)c);
+    double s0, c0;
+    sincos_full(a0, s0, c0);
+    return a0 + fma(s, c0, -(c * s0));
+}
+
 // ---- deep space (src/Sdp4Batch.zig:16-125,199-526; src/Sdp4.zig:681-866) --------------------------------
 // One record per deep-space satellite, read with warp-uniform loads (a warp works on one satellite).
 struct Sdp4Sat {
@@ -374,148 +386,199 @@ AZ_HD int resonance_node(double t) {
     return n;
 }
 
-// One deep-space cell.  (xli, xni) is the integrator state at lattice node atime = +-720*n nearest
-// below |t| (unused when irez == 0).  Returns a kernel-level status (0 ok, 1 decayed, 2 invalid ecc)
-// with the scalar path's checks (src/Sdp4.zig:913-967).
-AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double atime, const GravConsts &g,
-                    CellOut &o) {
+// kN deep-space cells of ONE satellite (kN epochs per thread, like sgp4_cell).  (xli, xni)[k] is the integrator state
+// at the lattice node atime[k] = +-720*n nearest below |t[k]| (unused when irez == 0).  st[k] receives a kernel-level
+// status (0 ok, 1 decayed, 2 invalid ecc) with the scalar path's checks (src/Sdp4.zig:913-967); a failing lane is
+// carried through with harmless operands so the other lanes are unaffected.
+// Every statement is a lane loop, so the two or three independent cells interleave on the fp64 pipe; the rare
+// alternatives (Lyddane low-inclination form, a large inclination excursion, a large resonance libration) are chosen by
+// flags folded over the lanes and fall back to per-lane code only when the lanes disagree.
+template <int kN>
+AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&xli)[kN], const double (&xni)[kN],
+                       const double (&atime)[kN], const GravConsts &g, CellOut (&o)[kN], int (&st)[kN]) {
     constexpr double zns = 1.19459e-5, znl = 1.5835218e-4, zes = 0.01675, zel = 0.05490;
-    const double t2 = t * t;
-    const double tempa = fma(-e.cc1, t, 1.0);
-    const double tempe = e.bc4 * t;
-    const double templ = e.t2cof * t2;
+    double tempa[kN], tempe[kN], templ[kN], mm[kN], argpm[kN], nodem[kN], em[kN], inclm[kN], am[kN];
+    AZ_LANES {
+        st[k] = 0;
+        const double t2 = t[k] * t[k];
+        tempa[k] = fma(-e.cc1, t[k], 1.0);
+        tempe[k] = e.bc4 * t[k];
+        templ[k] = e.t2cof * t2;
+        // secular gravity + drag, then luni-solar secular rates (src/Sdp4Batch.zig:212-236)
+        mm[k] = fma(e.dmdt, t[k], fma(e.mdot, t[k], e.mo));
+        argpm[k] = fma(e.domdt, t[k], fma(e.argpdot, t[k], e.argpo));
+        nodem[k] = fma(e.dnodt, t[k], fma(e.xnodcf, t2, fma(e.nodedot, t[k], e.nodeo)));
+        em[k] = fma(e.dedt, t[k], e.ecco);
+        inclm[k] = fma(e.didt, t[k], e.inclo);
+        am[k] = e.abase * tempa[k] * tempa[k];  // (xke / no)^(2/3) tempa^2 (src/Sdp4.zig:913-916 with nm = no)
+    }
 
-    // secular gravity + drag, then luni-solar secular rates (src/Sdp4Batch.zig:212-236)
-    double mm = fma(e.mdot, t, e.mo);
-    double argpm = fma(e.argpdot, t, e.argpo);
-    double nodem = fma(e.xnodcf, t2, fma(e.nodedot, t, e.nodeo));
-    double em = fma(e.dedt, t, e.ecco);
-    double inclm = fma(e.didt, t, e.inclo);
-    argpm = fma(e.domdt, t, argpm);
-    nodem = fma(e.dnodt, t, nodem);
-    mm = fma(e.dmdt, t, mm);
-    double nm = e.no;
-    double am = e.abase * tempa * tempa;  // (xke / no)^(2/3) tempa^2 (src/Sdp4.zig:913-916 with nm = no)
-
-    if (e.irez != 0) {  // final partial step from the lattice node (src/Sdp4.zig:803-819)
-        const double ft = t - atime;
-        double xndt, xnddt, xldot;
-        resonance_accel(e, xli, xni, atime, xndt, xnddt, xldot);
-        const double nmr = xni + xndt * ft + xnddt * ft * ft * 0.5;
-        const double xl = xli + xldot * ft + xndt * ft * ft * 0.5;
-        // theta = (gsto + t rptim) mod 2pi in the reference; the mean anomaly only ever enters a sine/cosine, whose
-        // range reduction absorbs the multiple of 2pi
-        const double theta = fma(t, kRptim, e.gsto);
-        mm = (e.irez == 2) ? xl - 2.0 * nodem + 2.0 * theta : xl - nodem - argpm + theta;
-        nm = e.no + (nmr - e.no);
-        if (nm <= 0.0) return 1;
-        // (xke / nm)^(2/3) = abase (1 + x)^(-2/3), x = (nm - no) / no: the resonance libration of the mean motion is a
-        // few 1e-4 of no, so a degree-6 binomial series replaces the reference's division + cube root
-        const double x = (nmr - e.no) * e.invNo;
-        if (abs_gt(x, 0x3f689374u)) {  // |x| > 3e-3 (never seen for catalogued objects): the general evaluation
-            const double cr = cbrt(g.xke / nm);
-            am = cr * cr * tempa * tempa;
-        } else {
-            double p = fma(x, 2618.0 / 6561.0, -308.0 / 729.0);  // binomial coefficients of (1 + x)^(-2/3)
-            p = fma(p, x, 110.0 / 243.0);
-            p = fma(p, x, -40.0 / 81.0);
-            p = fma(p, x, 5.0 / 9.0);
-            p = fma(p, x, -2.0 / 3.0);
-            am *= fma(p, x, 1.0);
+    if (e.irez != 0) {  // final partial step from the lattice node (src/Sdp4.zig:803-819); uniform: one satellite
+        double xndt[kN], xnddt[kN], xldot[kN];
+        AZ_LANES resonance_accel(e, xli[k], xni[k], atime[k], xndt[k], xnddt[k], xldot[k]);
+        AZ_LANES {
+            const double ft = t[k] - atime[k];
+            const double hft2 = 0.5 * ft * ft;
+            const double nmr = fma(xnddt[k], hft2, fma(xndt[k], ft, xni[k]));
+            const double xl = fma(xndt[k], hft2, fma(xldot[k], ft, xli[k]));
+            // theta = (gsto + t rptim) mod 2pi in the reference; the mean anomaly only ever enters a sine/cosine, whose
+            // range reduction absorbs the multiple of 2pi
+            const double theta = fma(t[k], kRptim, e.gsto);
+            mm[k] = (e.irez == 2) ? xl - 2.0 * nodem[k] + 2.0 * theta : xl - nodem[k] - argpm[k] + theta;
+            const double nm = e.no + (nmr - e.no);
+            if (nm <= 0.0) st[k] = 1;
+            // (xke / nm)^(2/3) = abase (1 + x)^(-2/3), x = (nm - no) / no: the resonance libration of the mean motion is
+            // a few 1e-4 of no, so a degree-6 binomial series replaces the reference's division + cube root
+            const double x = (nmr - e.no) * e.invNo;
+            if (abs_gt(x, 0x3f689374u)) {  // |x| > 3e-3 (never seen for catalogued objects): the general evaluation
+                const double cr = cbrt(g.xke / (nm > 0.0 ? nm : e.no));
+                am[k] = cr * cr * tempa[k] * tempa[k];
+            } else {
+                double p = fma(x, 2618.0 / 6561.0, -308.0 / 729.0);  // binomial coefficients of (1 + x)^(-2/3)
+                p = fma(p, x, 110.0 / 243.0);
+                p = fma(p, x, -40.0 / 81.0);
+                p = fma(p, x, 5.0 / 9.0);
+                p = fma(p, x, -2.0 / 3.0);
+                am[k] *= fma(p, x, 1.0);
+            }
         }
     }
 
-    em -= tempe;
-    if (em >= 1.0 || em < -0.001) return 2;
-    em = fmax(em, 1.0e-6);
-    if (am < 0.95) return 1;
-    mm = fma(e.no, templ, mm);
+    AZ_LANES {
+        em[k] -= tempe[k];
+        if (st[k] == 0 && (em[k] >= 1.0 || em[k] < -0.001)) st[k] = 2;
+        em[k] = fmax(em[k], 1.0e-6);
+        if (st[k] == 0 && am[k] < 0.95) st[k] = 1;
+        mm[k] = fma(e.no, templ[k], mm[k]);
+    }
 
     // luni-solar periodics, dpper (src/Sdp4.zig:681-759)
-    double sz, cz, sinzf, coszf;
-    // zf = zm + 2 ze sin(zm): the second sine/cosine is a rotation of the first by an angle below 2 ze
-    double zm = fma(zns, t, e.zmos);
-    sincos_full(zm, sz, cz);
+    double pe[kN], pinc[kN], pl[kN], pgh[kN], ph[kN];
     {
-        double sd, cd;
-        sincos_tiny(2.0 * zes * sz, sd, cd);  // |.| <= 0.0335
-        rotate(sz, cz, sd, cd, sinzf, coszf);
+        double sz[kN], cz[kN];
+        AZ_LANES sincos_full(fma(zns, t[k], e.zmos), sz[k], cz[k]);
+        AZ_LANES {
+            // zf = zm + 2 ze sin(zm): the second sine/cosine is a rotation of the first by an angle below 2 ze
+            double sd, cd, sinzf, coszf;
+            sincos_tiny(2.0 * zes * sz[k], sd, cd);  // |.| <= 0.0335
+            rotate(sz[k], cz[k], sd, cd, sinzf, coszf);
+            const double f2 = fma(0.5 * sinzf, sinzf, -0.25);
+            const double f3 = -0.5 * sinzf * coszf;
+            pe[k] = fma(e.se2, f2, e.se3 * f3);
+            pinc[k] = fma(e.si2, f2, e.si3 * f3);
+            pl[k] = fma(e.sl2, f2, fma(e.sl3, f3, e.sl4 * sinzf));
+            pgh[k] = fma(e.sgh2, f2, fma(e.sgh3, f3, e.sgh4 * sinzf));
+            ph[k] = fma(e.sh2, f2, e.sh3 * f3);
+        }
+        AZ_LANES sincos_full(fma(znl, t[k], e.zmol), sz[k], cz[k]);
+        AZ_LANES {
+            double sd, cd, sinzf, coszf;
+            sincos_quarter(2.0 * zel * sz[k], sd, cd);  // |.| <= 0.1098
+            rotate(sz[k], cz[k], sd, cd, sinzf, coszf);
+            const double f2 = fma(0.5 * sinzf, sinzf, -0.25);
+            const double f3 = -0.5 * sinzf * coszf;
+            pe[k] += fma(e.ee2, f2, e.e3 * f3);
+            pinc[k] += fma(e.xi2, f2, e.xi3 * f3);
+            pl[k] += fma(e.xl2, f2, fma(e.xl3, f3, e.xl4 * sinzf));
+            pgh[k] += fma(e.xgh2, f2, fma(e.xgh3, f3, e.xgh4 * sinzf));
+            ph[k] += fma(e.xh2, f2, e.xh3 * f3);
+        }
     }
-    double f2 = fma(0.5 * sinzf, sinzf, -0.25);
-    double f3 = -0.5 * sinzf * coszf;
-    double pe = e.se2 * f2 + e.se3 * f3;
-    double pinc = e.si2 * f2 + e.si3 * f3;
-    double pl = e.sl2 * f2 + e.sl3 * f3 + e.sl4 * sinzf;
-    double pgh = e.sgh2 * f2 + e.sgh3 * f3 + e.sgh4 * sinzf;
-    double ph = e.sh2 * f2 + e.sh3 * f3;
-    zm = fma(znl, t, e.zmol);
-    sincos_full(zm, sz, cz);
-    {
-        double sd, cd;
-        sincos_quarter(2.0 * zel * sz, sd, cd);  // |.| <= 0.1098
-        rotate(sz, cz, sd, cd, sinzf, coszf);
-    }
-    f2 = fma(0.5 * sinzf, sinzf, -0.25);
-    f3 = -0.5 * sinzf * coszf;
-    pe += e.ee2 * f2 + e.e3 * f3;
-    pinc += e.xi2 * f2 + e.xi3 * f3;
-    pl += e.xl2 * f2 + e.xl3 * f3 + e.xl4 * sinzf;
-    pgh += e.xgh2 * f2 + e.xgh3 * f3 + e.xgh4 * sinzf;
-    ph += e.xh2 * f2 + e.xh3 * f3;
 
-    const double dincl = fma(e.didt, t, pinc);  // inclm - inclo: luni-solar secular + periodic, ~1e-3 rad over years
-    inclm += pinc;
-    em += pe;
-    double sinip, cosip;
-    if (!abs_gt(dincl, kHiTiny)) {
-        double sd, cd;
-        sincos_tiny(dincl, sd, cd);
-        rotate(e.sinio, e.cosio, sd, cd, sinip, cosip);
+    double sinip[kN], cosip[kN];
+    bool smallInc = true, allNormal = true, allLyddane = true;
+    AZ_LANES {
+        const double dincl = fma(e.didt, t[k], pinc[k]);  // inclm - inclo: luni-solar secular + periodic, ~1e-3 rad over years
+        inclm[k] += pinc[k];
+        em[k] += pe[k];
+        smallInc &= !abs_gt(dincl, kHiTiny);
+        allNormal &= inclm[k] >= 0.2;
+        allLyddane &= !(inclm[k] >= 0.2);
+    }
+    if (smallInc) {  // the perturbed inclination is a small rotation away from the element set's
+        AZ_LANES {
+            double sd, cd;
+            sincos_tiny(fma(e.didt, t[k], pinc[k]), sd, cd);
+            rotate(e.sinio, e.cosio, sd, cd, sinip[k], cosip[k]);
+        }
     } else {
-        sincos_full(inclm, sinip, cosip);
+        AZ_LANES sincos_full(inclm[k], sinip[k], cosip[k]);
     }
-    if (inclm >= 0.2) {
-        ph = ph * rcp(sinip);
-        pgh = fma(-cosip, ph, pgh);
-        argpm += pgh;
-        nodem += ph;
-        mm += pl;
-    } else {  // Lyddane modification for near-equatorial orbits (src/Sdp4.zig:735-758)
-        nodem = mod_twopi(nodem);
-        double sinop, cosop;
-        sincos_full(nodem, sinop, cosop);
-        const double alfdp = sinip * sinop + (ph * cosop + pinc * cosip * sinop);
-        const double betdp = sinip * cosop + (-ph * sinop + pinc * cosip * cosop);
-        const double xls = mm + argpm + cosip * nodem;
-        const double dls = pl + pgh - pinc * nodem * sinip;
-        const double xnoh = nodem;
-        nodem = atan2(alfdp, betdp);
-        if (fabs(xnoh - nodem) > kPi) nodem += (nodem < xnoh) ? kTwoPi : -kTwoPi;
-        mm += pl;
-        argpm = xls + dls - mm - cosip * nodem;
+    if (allNormal) {
+        AZ_LANES {
+            const double phs = ph[k] * rcp(sinip[k]);
+            argpm[k] += fma(-cosip[k], phs, pgh[k]);
+            nodem[k] += phs;
+            mm[k] += pl[k];
+        }
+    } else {
+        // Lyddane modification for near-equatorial orbits (src/Sdp4.zig:735-758): the usual case for a geostationary
+        // belt object.  nodem <- atan2(alfdp, betdp): the vector is normalised and its angle taken with the fp32-seeded
+        // extraction of the geodetic epilogue instead of libdevice's atan2.
+        (void)allLyddane;
+        AZ_LANES {
+            if (inclm[k] >= 0.2) {
+                const double phs = ph[k] * rcp(sinip[k]);
+                argpm[k] += fma(-cosip[k], phs, pgh[k]);
+                nodem[k] += phs;
+                mm[k] += pl[k];
+            } else {
+                const double nod = mod_twopi(nodem[k]);
+                double sinop, cosop;
+                sincos_full(nod, sinop, cosop);
+                const double alfdp = sinip[k] * sinop + (ph[k] * cosop + pinc[k] * cosip[k] * sinop);
+                const double betdp = sinip[k] * cosop + (-ph[k] * sinop + pinc[k] * cosip[k] * cosop);
+                const double xls = mm[k] + argpm[k] + cosip[k] * nod;
+                const double dls = pl[k] + pgh[k] - pinc[k] * nod * sinip[k];
+                const double r2 = fma(alfdp, alfdp, betdp * betdp);
+                double nn;
+                if (r2 > 1.0e-280) {
+                    const double ir = rsqrt_nr(r2);
+                    nn = angle_of_unit(alfdp * ir, betdp * ir);
+                } else {
+                    nn = 0.0;  // atan2(0, 0)
+                }
+                if (fabs(nod - nn) > kPi) nn += (nn < nod) ? kTwoPi : -kTwoPi;
+                nodem[k] = nn;
+                mm[k] += pl[k];
+                argpm[k] = xls + dls - mm[k] - cosip[k] * nn;
+            }
+        }
     }
-    if (inclm < 0.0) {  // src/Sdp4.zig:932-936 (sin flips sign with the inclination, cos does not)
-        sinip = -sinip;
-        nodem += kPi;
-        argpm -= kPi;
+    SatAngles sa[kN];
+    AZ_LANES {
+        if (inclm[k] < 0.0) {  // src/Sdp4.zig:932-936 (sin flips sign with the inclination, cos does not)
+            sinip[k] = -sinip[k];
+            nodem[k] += kPi;
+            argpm[k] -= kPi;
+        }
+        em[k] = fmax(em[k], 1.0e-6);
+        if (st[k] == 0 && em[k] >= 1.0) st[k] = 2;
+        if (em[k] >= 1.0) em[k] = 0.5;  // failing lane: keep the shared Kepler loop well conditioned
+        if (!(am[k] >= 0.95)) am[k] = 1.0;
+        // inclination-dependent terms re-derived per cell (src/Sdp4Batch.zig:326-339)
+        const double cosip2 = cosip[k] * cosip[k];
+        const double den = 1.0 + cosip[k];
+        sa[k].sinio = sinip[k];
+        sa[k].cosio = cosip[k];
+        sa[k].aycof = -0.5 * g.j3oj2 * sinip[k];
+        sa[k].xlcof = -0.25 * g.j3oj2 * sinip[k] * fma(5.0, cosip[k], 3.0) * rcp(fabs(den) > 1.5e-12 ? den : 1.5e-12);
+        sa[k].x1mth2 = 1.0 - cosip2;
+        sa[k].fold(fma(3.0, cosip2, -1.0), fma(7.0, cosip2, -1.0));
     }
-    em = fmax(em, 1.0e-6);
-    if (em >= 1.0) return 2;
+    kepler_posvel<kN>(am, em, mm, argpm, nodem, sa, g, o);
+    AZ_LANES if (st[k] == 0 && o[k].mrt < 1.0) st[k] = 1;
+}
 
-    // inclination-dependent terms re-derived per cell (src/Sdp4Batch.zig:326-339)
-    const double cosip2 = cosip * cosip;
-    const double aycof = -0.5 * g.j3oj2 * sinip;
-    const double den = 1.0 + cosip;
-    const double xlcof = -0.25 * g.j3oj2 * sinip * fma(5.0, cosip, 3.0) * rcp(fabs(den) > 1.5e-12 ? den : 1.5e-12);
-    const double am1[1] = {am}, em1[1] = {em}, mm1[1] = {mm}, ar1[1] = {argpm}, no1[1] = {nodem};
-    SatAngles sa[1];
-    sa[0].sinio = sinip; sa[0].cosio = cosip; sa[0].aycof = aycof; sa[0].xlcof = xlcof;
-    sa[0].x1mth2 = 1.0 - cosip2;
-    sa[0].fold(fma(3.0, cosip2, -1.0), fma(7.0, cosip2, -1.0));
+// One deep-space cell (the single-epoch form of the above).
+AZ_HD int sdp4_cell(const Sdp4Sat &e, double t, double xli, double xni, double atime, const GravConsts &g,
+                    CellOut &o) {
+    const double t1[1] = {t}, l1[1] = {xli}, n1[1] = {xni}, a1[1] = {atime};
     CellOut o1[1];
-    kepler_posvel<1>(am1, em1, mm1, ar1, no1, sa, g, o1);
+    int st[1];
+    sdp4_cell_n<1>(e, t1, l1, n1, a1, g, o1, st);
     o = o1[0];
-    return (o.mrt < 1.0) ? 1 : 0;
+    return st[0];
 }
 
 // ---- output-mode epilogue (src/Constellation.zig:478-509, src/WorldCoordinateSystem.zig:98-121) ----
@@ -524,18 +587,6 @@ AZ_HD void eci_to_ecef(double &x, double &y, double sinG, double cosG) {
     const double ey = fma(y, cosG, -(x * sinG));
     x = ex;
     y = ey;
-}
-
-// Angle of the unit vector (s, c) = (sin a, cos a), a in (-pi, pi]: the fp32 arctangent (idle FMA/XU pipes) is the
-// seed, exactly representable in fp64; one first-order correction with the fp64 sincos of the seed finishes it:
-// d = sin(a - a0) = s cos a0 - c sin a0, |d| < 1e-6, asin(d) - d < 2e-19.  22 fp64 instructions against ~54 for
-// libdevice's atan2 (and no constants to materialise).  The sign of a zero s survives the conversion, so the branch
-// cut at +-pi falls where atan2 puts it.
-AZ_HD double angle_of_unit(double s, double c) {
-    const double a0 = (double)atan2f((float)s, (float)c);
-    double s0, c0;
-    sincos_full(a0, s0, c0);
-    return a0 + fma(s, c0, -(c * s0));
 }
 
 // ECEF -> (geodetic latitude rad, longitude rad, altitude km) on WGS84.  The reference iterates

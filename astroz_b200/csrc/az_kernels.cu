@@ -175,8 +175,8 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t t0 = blockIdx.y * kStripe;
-    const uint32_t t1 = min(t0 + (uint32_t)kStripe, a.nTimes);
+    const uint32_t t0 = blockIdx.y * a.stripe;
+    const uint32_t t1 = min(t0 + a.stripe, a.nTimes);
     double *stage = stageAll + (kGather != 0 ? warp * 2 * kStageDoubles : 0);
     mbar_wait(&bar, 0);
 
@@ -374,12 +374,41 @@ int sgp4_variant_count() { return 0; }
 const char *sgp4_variant_name(int) { return "?"; }
 #endif
 
+// resident CTA slots of the current device for the near-earth grid (3 CTAs of 128 threads per SM at 158 registers)
+static int k1_resident_slots() {
+    static int cached[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148 * 3;
+    if (cached[dev] == 0) {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        cached[dev] = sms * 3;
+    }
+    return cached[dev];
+}
+static uint32_t g_k1StripeOverride = 0;  // measurement only (ASTROZ_K1_STRIPE): epochs per CTA, 0 = automatic
+void set_sgp4_stripe(uint32_t epochs) { g_k1StripeOverride = epochs; }
+
 template <int kLayout, int kMode, bool kVel, int kWarps, int kStripe, int kMinBlocks, int kLanes, int kGather = 0>
-static cudaError_t launch_k1(const GridArgs &a, cudaStream_t stream) {
-    const uint32_t tiles = (a.nSats + kTileSats - 1) / kTileSats;
-    const uint32_t stripes = (a.nTimes + kStripe - 1) / kStripe;
-    if (tiles == 0 || stripes == 0) return cudaSuccess;
-    dim3 grid(tiles, stripes);
+static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
+    const uint32_t tiles = (a0.nSats + kTileSats - 1) / kTileSats;
+    if (tiles == 0 || a0.nTimes == 0) return cudaSuccess;
+    // Epochs per CTA.  kStripe is the shape's stripe for a grid that fills the GPU many times over (fewest CTA
+    // prologues: barrier, TMA tile copy).  A small grid -- a 1/8 satellite shard of the headline catalog is 211 tiles --
+    // is cut finer, down to one pass of the CTA's warps (32 * kLanes epochs), until it gives every SM's resident CTA
+    // slots about eight CTAs each, so that the last, partly filled wave is a small fraction of the launch.
+    GridArgs a = a0;
+    constexpr uint32_t kPass = 32 * kLanes;
+    uint32_t stripe = kStripe;
+    const uint32_t slots = (uint32_t)k1_resident_slots();
+    while (stripe > kPass && (uint64_t)tiles * ((a.nTimes + stripe - 1) / stripe) < 8ull * slots) {
+        const uint32_t half = ((stripe / 2 + kPass - 1) / kPass) * kPass;
+        if (half >= stripe) break;
+        stripe = half;
+    }
+    if (g_k1StripeOverride) stripe = std::max(kPass, g_k1StripeOverride / kPass * kPass);
+    a.stripe = stripe;
+    dim3 grid(tiles, (a.nTimes + stripe - 1) / stripe);
     sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks, kLanes, kGather>
         <<<grid, kWarps * 32, 0, stream>>>(a);
     return cudaGetLastError();
@@ -503,6 +532,8 @@ cudaError_t launch_sdp4_lattice(const Sdp4Sat *sats, uint32_t nSats, double2 *la
 constexpr int kSdp4Threads = 128;
 constexpr int kSdp4Stripe = 512;
 
+constexpr int kSdp4Lanes = 2;  // epochs per thread, 32 apart (each warp-run is 32 consecutive epochs, like K1)
+
 template <int kLayout, int kMode, bool kVel, int kGather, int kMinBlocks>
 __global__ void __launch_bounds__(kSdp4Threads, kMinBlocks) sdp4_grid_kernel(const GridArgs a) {
     __shared__ Sdp4Sat e;
@@ -519,42 +550,55 @@ __global__ void __launch_bounds__(kSdp4Threads, kMinBlocks) sdp4_grid_kernel(con
     const uint32_t row = __ldg(a.orig + sat);
     const uint32_t t0 = blockIdx.y * kSdp4Stripe;
     const uint32_t t1 = min(t0 + (uint32_t)kSdp4Stripe, a.nTimes);
+    constexpr uint32_t kRun = 32 * kSdp4Lanes;
 #pragma unroll 1
-    for (uint32_t tw = t0 + warp * 32; tw < t1; tw += kSdp4Threads) {  // warp-uniform
-        const uint32_t t = tw + lane;
-        const bool valid = t < t1;
-        const uint32_t tc = min(t, t1 - 1);
-        const double ts = a.tsince ? __ldg(a.tsince + tc)
-                                   : (__ldg(a.jdFull + tc) - e.epochJd) * 1440.0;  // src/Constellation.zig:465
-        double xli = e.xlamo, xni = e.no, atime = 0.0;
-        if (e.irez != 0) {
-            const int node = resonance_node(ts);
-            const int have = min(node, a.latticeNodes - 1);
-            const double2 st = __ldg(a.lattice + ((size_t)sat * 2 + (ts > 0.0 ? 0 : 1)) * a.latticeNodes + have);
-            const double delt = ts > 0.0 ? kStepp : -kStepp;
-            xli = st.x;
-            xni = st.y;
-            atime = delt * (double)have;
-            for (int k = have; k < node; ++k) resonance_step(e, xli, xni, atime, delt);  // beyond the lattice
+    for (uint32_t tw = t0 + warp * kRun; tw < t1; tw += (kSdp4Threads / 32) * kRun) {  // warp-uniform
+        double ts[kSdp4Lanes], xli[kSdp4Lanes], xni[kSdp4Lanes], atime[kSdp4Lanes];
+#pragma unroll
+        for (int k = 0; k < kSdp4Lanes; ++k) {
+            const uint32_t tc = min(tw + 32u * k + lane, t1 - 1);
+            ts[k] = a.tsince ? __ldg(a.tsince + tc)
+                             : (__ldg(a.jdFull + tc) - e.epochJd) * 1440.0;  // src/Constellation.zig:465
+            xli[k] = e.xlamo;
+            xni[k] = e.no;
+            atime[k] = 0.0;
+            if (e.irez != 0) {
+                const int node = resonance_node(ts[k]);
+                const int have = min(node, a.latticeNodes - 1);
+                const double2 st = __ldg(a.lattice + ((size_t)sat * 2 + (ts[k] > 0.0 ? 0 : 1)) * a.latticeNodes + have);
+                const double delt = ts[k] > 0.0 ? kStepp : -kStepp;
+                xli[k] = st.x;
+                xni[k] = st.y;
+                atime[k] = delt * (double)have;
+                for (int j = have; j < node; ++j) resonance_step(e, xli[k], xni[k], atime[k], delt);  // beyond the lattice
+            }
         }
-        CellOut o;
-        const int st = sdp4_cell(e, ts, xli, xni, atime, a.g, o);
-        if (valid && a.status) a.status[(size_t)row * a.nTimes + t] = (uint8_t)st;
-        if (st != 0) {  // zero fill, per satellite (src/Constellation.zig:468-471,511-528 does it per batch of 8)
-            o.rx = o.ry = o.rz = o.vx = o.vy = o.vz = 0.0;
-        } else if (valid) {
-            to_output_frame<kMode, kVel>(a, t, o);
-        }
-        if (kGather != 0) {
-            emit_run_sat_major<kVel, kGather>(a, row, tw, min(32u, t1 - tw), lane, valid, o, stage);
-        } else if (valid) {
-            store_direct<kLayout, kVel>(a, row, t, o);
+        CellOut o[kSdp4Lanes];
+        int st[kSdp4Lanes];
+        sdp4_cell_n<kSdp4Lanes>(e, ts, xli, xni, atime, a.g, o, st);
+#pragma unroll
+        for (int k = 0; k < kSdp4Lanes; ++k) {
+            const uint32_t twk = tw + 32u * k;
+            if (twk >= t1) break;  // warp-uniform
+            const uint32_t t = twk + lane;
+            const bool valid = t < t1;
+            if (valid && a.status) a.status[(size_t)row * a.nTimes + t] = (uint8_t)st[k];
+            if (st[k] != 0) {  // zero fill, per satellite (src/Constellation.zig:468-471,511-528 does it per batch of 8)
+                o[k].rx = o[k].ry = o[k].rz = o[k].vx = o[k].vy = o[k].vz = 0.0;
+            } else if (valid) {
+                to_output_frame<kMode, kVel>(a, t, o[k]);
+            }
+            if (kGather != 0) {
+                emit_run_sat_major<kVel, kGather>(a, row, twk, min(32u, t1 - twk), lane, valid, o[k], stage);
+            } else if (valid) {
+                store_direct<kLayout, kVel>(a, row, t, o[k]);
+            }
         }
     }
 }
 
 #ifndef AZ_DEFAULT_K2_BLOCKS
-#define AZ_DEFAULT_K2_BLOCKS 5
+#define AZ_DEFAULT_K2_BLOCKS 3
 #endif
 static int g_k2Variant = -1;  // tuning only (ASTROZ_SDP4_VARIANT): 0 -> 3, 1 -> 4, 2 -> 5 resident CTAs per SM
 void set_sdp4_variant(int v) { g_k2Variant = v; }

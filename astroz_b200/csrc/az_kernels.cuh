@@ -29,6 +29,7 @@ struct GridArgs {
     const double *gsin = nullptr;        // sin/cos(GMST) per epoch when mode != TEME
     const double *gcos = nullptr;
     uint32_t nTimes = 0;
+    uint32_t stripe = 0;                 // K1: epochs per CTA, chosen at launch from the CTA count (0 = the shape's default)
     // outputs
     double *pos = nullptr;
     double *vel = nullptr;               // nullable
@@ -102,6 +103,7 @@ cudaError_t fp64_pipe_peak(double *flops);
 
 int sgp4_variant_count();
 void set_sdp4_variant(int v);
+void set_sgp4_stripe(uint32_t epochs);  // measurement only: fixed epochs per CTA for the near-earth grid, 0 = automatic
 const char *sgp4_variant_name(int variant);
 
 }  // namespace az

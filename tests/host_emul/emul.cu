@@ -53,20 +53,32 @@ extern "C" int emul_constellation_propagate(const char *const *l1, const char *c
     for (uint32_t s = 0; s < cat.nSdp4; ++s) {
         const Sdp4Sat &e = cat.sdp4[s];
         const uint32_t orig = cat.sdp4Orig[s];
-        for (uint32_t t = 0; t < nt; ++t) {
-            const double ts = (jdFull[t] - e.epochJd) * 1440.0;
-            double xli = e.xlamo, xni = e.no, atime = 0.0;
-            if (e.irez != 0) {
-                const int node = resonance_node(ts);
-                const double delt = ts > 0.0 ? kStepp : -kStepp;
-                for (int k = 0; k < node; ++k) resonance_step(e, xli, xni, atime, delt);
+        for (uint32_t t = 0; t < nt; t += g_lanes) {
+            double ts[2], xli[2], xni[2], atime[2];
+            for (int k = 0; k < 2; ++k) {  // the kernel's lattice walk, from node 0 (no lattice cache on the host)
+                const uint32_t tk = t + k < nt ? t + k : nt - 1;
+                ts[k] = (jdFull[tk] - e.epochJd) * 1440.0;
+                xli[k] = e.xlamo; xni[k] = e.no; atime[k] = 0.0;
+                if (e.irez != 0) {
+                    const int node = resonance_node(ts[k]);
+                    const double delt = ts[k] > 0.0 ? kStepp : -kStepp;
+                    for (int j = 0; j < node; ++j) resonance_step(e, xli[k], xni[k], atime[k], delt);
+                }
             }
-            CellOut o{};
-            int st = sdp4_cell(e, ts, xli, xni, atime, g, o);
-            double *p = pos + ((size_t)orig * nt + t) * 3, *v = vel + ((size_t)orig * nt + t) * 3;
-            if (st != 0) { p[0] = p[1] = p[2] = v[0] = v[1] = v[2] = 0.0; }
-            else { p[0] = o.rx; p[1] = o.ry; p[2] = o.rz; v[0] = o.vx; v[1] = o.vy; v[2] = o.vz; }
-            if (status) status[(size_t)orig * nt + t] = (uint8_t)st;
+            CellOut oo[2];
+            int st[2] = {0, 0};
+            if (g_lanes == 2) {  // the kernel's 2-epochs-per-thread path
+                sdp4_cell_n<2>(e, ts, xli, xni, atime, g, oo, st);
+            } else {
+                st[0] = sdp4_cell(e, ts[0], xli[0], xni[0], atime[0], g, oo[0]);
+            }
+            for (int k = 0; k < g_lanes && t + k < nt; ++k) {
+                const CellOut &o = oo[k];
+                double *p = pos + ((size_t)orig * nt + t + k) * 3, *v = vel + ((size_t)orig * nt + t + k) * 3;
+                if (st[k] != 0) { p[0] = p[1] = p[2] = v[0] = v[1] = v[2] = 0.0; }
+                else { p[0] = o.rx; p[1] = o.ry; p[2] = o.rz; v[0] = o.vx; v[1] = o.vy; v[2] = o.vz; }
+                if (status) status[(size_t)orig * nt + t + k] = (uint8_t)st[k];
+            }
         }
     }
     return 0;

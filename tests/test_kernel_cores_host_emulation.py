@@ -66,10 +66,13 @@ def test_cores_match_oracle_all_classes(emul, oracle):
     for tles in (synth.near_earth_catalog(400), synth.mixed_catalog(300, n_geo=60, n_molniya=40, n_gps=40),
                  [G.ISS, G.GEO28626, G.SAT55909, G.GPS20413, G.SAT55910, G.HEO09880]):
         po, vo, err, klass = oracle.constellation_propagate(tles, jd, fr)
-        pe, ve, st = emul(tles, jd, fr)
-        assert np.max(np.abs(po - pe)) < 1e-6 and np.max(np.abs(vo - ve)) < 1e-9
-        deep = klass > 0
-        assert np.array_equal(st[deep], err[deep])
+        for lanes in (1, 2):     # one epoch per thread, and the kernels' two-epochs-per-thread form of both cores
+            emul.lib.emul_set_lanes(lanes)
+            pe, ve, st = emul(tles, jd, fr)
+            assert np.max(np.abs(po - pe)) < 1e-6 and np.max(np.abs(vo - ve)) < 1e-9
+            deep = klass > 0
+            assert np.array_equal(st[deep], err[deep])
+        emul.lib.emul_set_lanes(1)
 
 
 def test_cores_error_cells(emul, oracle):
@@ -79,11 +82,14 @@ def test_cores_error_cells(emul, oracle):
     jd = np.full(40, 2460430.5)
     fr = np.linspace(0.0, 2000.0, 40)
     po, vo, err, _ = oracle.constellation_propagate([G.GPS20413, bad], jd, fr)
-    pe, ve, st = emul([G.GPS20413, bad], jd, fr)
-    assert err[1].any() and np.array_equal(st, err)
-    assert np.all(pe[1][err[1] != 0] == 0.0)
-    ok = err == 0
-    assert np.max(np.abs(po[ok] - pe[ok])) < 1e-5
+    for lanes in (1, 2):         # a failing lane must not disturb the cell sharing its thread
+        emul.lib.emul_set_lanes(lanes)
+        pe, ve, st = emul([G.GPS20413, bad], jd, fr)
+        assert err[1].any() and np.array_equal(st, err)
+        assert np.all(pe[1][err[1] != 0] == 0.0)
+        ok = err == 0
+        assert np.max(np.abs(po[ok] - pe[ok])) < 1e-5
+    emul.lib.emul_set_lanes(1)
 
 
 def test_geodetic_epilogue_matches_reference_iteration(emul, oracle):
