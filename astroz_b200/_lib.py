@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
         "astroz_cuda_last_error": (C.c_char_p, []),
         "astroz_cuda_host_alloc": (vp, [C.c_size_t]),
         "astroz_cuda_host_free": (None, [vp]),
+        "astroz_cuda_host_register": (i32, [vp, C.c_size_t]),
+        "astroz_cuda_host_unregister": (i32, [vp]),
         "astroz_cuda_constellation_create": (i32, [C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), u32, i32, i32,
                                                    C.POINTER(vp)]),
         "astroz_cuda_constellation_create_from_text": (i32, [C.c_char_p, C.c_size_t, i32, i32, C.POINTER(vp)]),
@@ -124,7 +126,7 @@ EXPORTS = [
     "astroz_cuda_sgp4_free", "astroz_cuda_sgp4_is_deep_space", "astroz_cuda_sgp4_epoch", "astroz_cuda_sgp4_elements",
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",
     "astroz_cuda_fp64_peak", "astroz_cuda_fp64_pipe_peak", "astroz_cuda_constellation_devices",
-    "astroz_cuda_constellation_propagate_replicated",
+    "astroz_cuda_constellation_propagate_replicated", "astroz_cuda_host_register", "astroz_cuda_host_unregister",
 ]
 
 
@@ -213,6 +215,16 @@ def pinned_empty(shape, dtype=np.float64) -> np.ndarray:
     n = int(np.prod(shape)) if shape else 1
     block = _PinnedBlock(n * dtype.itemsize)
     return np.asarray(block)[: n * dtype.itemsize].view(dtype).reshape(shape)
+
+
+def host_register(a: np.ndarray) -> None:
+    """Page-lock a caller-owned array in place (cudaHostRegister) so results reach it by direct DMA; undo with
+    host_unregister before the array is freed."""
+    check(lib().astroz_cuda_host_register(C.c_void_p(a.ctypes.data), a.nbytes))
+
+
+def host_unregister(a: np.ndarray) -> None:
+    check(lib().astroz_cuda_host_unregister(C.c_void_p(a.ctypes.data)))
 
 
 def device_count() -> int:

@@ -9,8 +9,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "az_ingest.cuh"
@@ -50,6 +56,111 @@ int32_t status_to_code(int st) {  // kernel-level code -> C API code (src/c_api/
         case az::kBadTle: return ASTROZ_BAD_TLE_LENGTH;
         default: return ASTROZ_UNKNOWN;
     }
+}
+
+// ---- delivery into caller-owned PAGEABLE host memory --------------------------------------------------------------
+// The reference writes into whatever slices the caller hands in (src/Constellation.zig:245-258; the Python layer
+// passes plain numpy buffers, bindings/python/src/satrec.zig:917-942).  A device->host DMA into pageable memory is
+// staged by the driver through a small internal buffer, synchronously, at a fraction of the PCIe rate.  Instead the
+// result leaves the GPU in pieces into a ring of pinned slots owned by the handle (full-rate DMA), and a small pool of
+// host threads copies each landed piece to its final place while the next pieces are in flight.
+constexpr size_t kPieceBytes = 8u << 20;
+constexpr int kRingSlots = 4;
+
+class CopyPool {  // process-wide, created on first use, never destroyed (workers sleep on the condition variable)
+public:
+    static CopyPool &get() {
+        static CopyPool *p = new CopyPool();
+        return *p;
+    }
+    int threads() const { return (int)workers_.size(); }
+    // copy `rows` rows of rowBytes from a contiguous source to a destination with pitch hpitch, split over the pool
+    void copy(char *dst, const char *src, size_t rows, size_t rowBytes, size_t hpitch) {
+        const size_t total = rows * rowBytes;
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>(workers_.size(), total / (256u << 10)));
+        if (parts <= 1 || workers_.empty()) {
+            run(dst, src, 0, rows, rowBytes, hpitch, 0, total);
+            return;
+        }
+        std::atomic<int> left(parts);
+        std::mutex dm;
+        std::condition_variable dcv;
+        for (int k = 0; k < parts; ++k) {
+            const size_t b0 = total * k / parts, b1 = total * (k + 1) / parts;
+            push([=, &left, &dm, &dcv] {
+                run(dst, src, 0, rows, rowBytes, hpitch, b0, b1);
+                if (left.fetch_sub(1) == 1) {
+                    std::lock_guard<std::mutex> g(dm);
+                    dcv.notify_one();
+                }
+            });
+        }
+        std::unique_lock<std::mutex> g(dm);
+        dcv.wait(g, [&] { return left.load() == 0; });
+    }
+
+private:
+    CopyPool() {
+        int n = 8;
+        if (const char *v = std::getenv("ASTROZ_COPY_THREADS")) n = std::max(0, std::min(64, std::atoi(v)));
+        const unsigned hw = std::thread::hardware_concurrency();
+        if (hw && (unsigned)n > hw) n = (int)hw;
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+        for (auto &t : workers_) t.detach();
+    }
+    // bytes [b0, b1) of the logical contiguous source, scattered to rows of the destination
+    static void run(char *dst, const char *src, size_t, size_t, size_t rowBytes, size_t hpitch, size_t b0, size_t b1) {
+        if (hpitch == rowBytes) {
+            std::memcpy(dst + b0, src + b0, b1 - b0);
+            return;
+        }
+        size_t b = b0;
+        while (b < b1) {
+            const size_t r = b / rowBytes, o = b % rowBytes;
+            const size_t len = std::min(rowBytes - o, b1 - b);
+            std::memcpy(dst + r * hpitch + o, src + b, len);
+            b += len;
+        }
+    }
+    void push(std::function<void()> f) {
+        {
+            std::lock_guard<std::mutex> g(m_);
+            q_.push_back(std::move(f));
+        }
+        cv_.notify_one();
+    }
+    void loop() {
+        for (;;) {
+            std::function<void()> f;
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&] { return !q_.empty(); });
+                f = std::move(q_.front());
+                q_.pop_front();
+            }
+            f();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+};
+
+struct Piece {  // one ring-sized piece of a deferred delivery: rows x rowBytes, contiguous on the device
+    const char *dsrc;
+    char *hdst;
+    size_t rows, rowBytes, hpitch;
+    int chunk;  // the grid chunk whose kernels produce it (chunkDone[chunk])
+};
+
+bool is_pageable(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
 }
 
 template <typename T>
@@ -133,6 +244,10 @@ struct Constellation {
     std::vector<uint32_t> shardDeep0;  // first deep-space index of each shard, plus the end
     DevBuf<double> dFullPos, dFullVel; // per shard: the WHOLE block, for the replicated (all-gather) propagate
     bool multi() const { return !shards.empty(); }
+    // deferred delivery into pageable host memory (see CopyPool)
+    std::vector<Piece> plan;
+    char *ring = nullptr;
+    cudaEvent_t ringEv[kRingSlots] = {};
 
     ~Constellation() {
         for (Constellation *sh : shards) delete sh;
@@ -143,6 +258,8 @@ struct Constellation {
         dSdp4.release(); dTime.release(); dToffCall.release(); dMask.release(); dLattice.release(); dPos.release(); dVel.release();
         dHead.release(); dNext.release(); dPairs.release(); dTIdx.release(); dCount.release();
         dFullPos.release(); dFullVel.release();
+        if (ring) cudaFreeHost(ring);
+        for (auto &e : ringEv) if (e) cudaEventDestroy(e);
         for (auto &h : hTimeSlot) if (h) cudaFreeHost(h);
         if (hToffCall) cudaFreeHost(hToffCall);
         for (auto &e : slotCopied) if (e) cudaEventDestroy(e);
@@ -974,6 +1091,77 @@ int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, con
     return rc;
 }
 
+// Send `rows` rows of rowBytes (contiguous on the device at dsrc) to the host at hdst with pitch hpitch, after the
+// kernels of grid chunk `chunk`.  Pinned / registered destinations get the copy queued on the copy stream right away;
+// pageable ones are recorded as ring-sized pieces and delivered by run_ring() in the wait half of the call.
+static int32_t deliver(Constellation *c, bool pageable, int chunk, const double *dsrc, double *hdst, size_t rows,
+                       size_t rowBytes, size_t hpitch) {
+    if (!pageable) {
+        if (rows == 1 || hpitch == rowBytes)
+            AZ_CUDA(cudaMemcpyAsync(hdst, dsrc, rows * rowBytes, cudaMemcpyDeviceToHost, c->copyStream));
+        else
+            AZ_CUDA(cudaMemcpy2DAsync(hdst, hpitch, dsrc, rowBytes, rowBytes, rows, cudaMemcpyDeviceToHost, c->copyStream));
+        return ASTROZ_OK;
+    }
+    const char *src = reinterpret_cast<const char *>(dsrc);
+    char *dst = reinterpret_cast<char *>(hdst);
+    if (rows == 1 || hpitch == rowBytes) {  // one contiguous run: cut by bytes
+        const size_t total = rows * rowBytes;
+        for (size_t b = 0; b < total; b += kPieceBytes)
+            c->plan.push_back(Piece{src + b, dst + b, 1, std::min(kPieceBytes, total - b), std::min(kPieceBytes, total - b), chunk});
+    } else if (rowBytes > kPieceBytes) {     // very wide rows: each row cut by bytes
+        for (size_t r = 0; r < rows; ++r)
+            for (size_t b = 0; b < rowBytes; b += kPieceBytes)
+                c->plan.push_back(Piece{src + r * rowBytes + b, dst + r * hpitch + b, 1, std::min(kPieceBytes, rowBytes - b),
+                                        std::min(kPieceBytes, rowBytes - b), chunk});
+    } else {                                // whole rows per piece
+        const size_t per = std::max<size_t>(1, kPieceBytes / rowBytes);
+        for (size_t r = 0; r < rows; r += per)
+            c->plan.push_back(Piece{src + r * rowBytes, dst + r * hpitch, std::min(per, rows - r), rowBytes, hpitch, chunk});
+    }
+    return ASTROZ_OK;
+}
+
+// Drain the deferred deliveries of one handle: up to kRingSlots pieces in flight over PCIe while the pool copies the
+// landed one to its final place.
+static int32_t run_ring(Constellation *c) {
+    if (c->plan.empty()) return ASTROZ_OK;
+    AZ_CUDA(cudaSetDevice(c->device));
+    if (!c->ring) {
+        AZ_CUDA(cudaMallocHost(&c->ring, kPieceBytes * kRingSlots));
+        for (auto &e : c->ringEv) AZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    CopyPool &pool = CopyPool::get();
+    const size_t n = c->plan.size();
+    auto issue = [&](size_t i) -> cudaError_t {
+        const Piece &p = c->plan[i];
+        const int slot = (int)(i % kRingSlots);
+        cudaError_t e = cudaStreamWaitEvent(c->copyStream, c->chunkDone[p.chunk], 0);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(c->ring + (size_t)slot * kPieceBytes, p.dsrc, p.rows * p.rowBytes, cudaMemcpyDeviceToHost,
+                                c->copyStream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ringEv[slot], c->copyStream);
+        return e;
+    };
+    cudaError_t e = cudaSuccess;
+    for (size_t i = 0; i < std::min<size_t>(kRingSlots, n) && e == cudaSuccess; ++i) e = issue(i);
+    for (size_t i = 0; i < n && e == cudaSuccess; ++i) {
+        const int slot = (int)(i % kRingSlots);
+        e = cudaEventSynchronize(c->ringEv[slot]);
+        if (e != cudaSuccess) break;
+        const Piece &p = c->plan[i];
+        pool.copy(p.hdst, c->ring + (size_t)slot * kPieceBytes, p.rows, p.rowBytes, p.hpitch);
+        if (i + kRingSlots < n) e = issue(i + kRingSlots);
+    }
+    c->plan.clear();
+    if (e != cudaSuccess) return cuda_fail(e, "pageable delivery ring");
+    return ASTROZ_OK;
+}
+
+// Wait half for several handles at once (the shards of a multi-device handle): rings are drained side by side, one
+// host thread per shard, so every PCIe link stays busy.
+static int32_t wait_all(const std::vector<Constellation *> &hs);
+
 // Host-buffer propagate, split in two so a multi-device handle can queue every shard before waiting on any:
 // queue = upload the time axis, launch the grid in chunks, start each chunk's device->host copy as soon as its kernels
 // finish; wait = drain the streams.  This handle's rows land at rows [rowOffset, rowOffset + n) of a host block with
@@ -1003,6 +1191,8 @@ static int32_t propagate_host_queue(Constellation *c, const double *jd, const do
     uint32_t nChunks = (bySat || byTime) ? std::min<uint32_t>((uint32_t)c->chunks, units) : 1;
     if (total * 8 < (8u << 20)) nChunks = 1;
     const uint32_t per = (units + nChunks - 1) / nChunks;
+    const bool posPageable = is_pageable(pos), velPageable = vel && is_pageable(vel);
+    c->plan.clear();
     AZ_CUDA(cudaEventRecord(c->ev[4], s));  // whole-call span: first kernel of the first chunk ...
     for (uint32_t k = 0; k < nChunks; ++k) {
         const uint32_t u0 = k * per, u1 = std::min(units, u0 + per);
@@ -1030,16 +1220,16 @@ static int32_t propagate_host_queue(Constellation *c, const double *jd, const do
         for (int which = 0; which < (vel ? 2 : 1); ++which) {
             double *hdst = which ? vel : pos;
             const double *dsrc = (which ? dVel : dPos) + off;
+            const bool pg = which ? velPageable : posPageable;
             if (layout == 0) {  // this handle's rows are one contiguous run of the (possibly wider) host block
-                AZ_CUDA(cudaMemcpyAsync(hdst + (size_t)rowOffset * n_times * 3 + off, dsrc, cnt * 8,
-                                        cudaMemcpyDeviceToHost, c->copyStream));
+                rc = deliver(c, pg, (int)k, dsrc, hdst + (size_t)rowOffset * n_times * 3 + off, 1, cnt * 8, cnt * 8);
             } else if (totalRows == n) {
-                AZ_CUDA(cudaMemcpyAsync(hdst + off, dsrc, cnt * 8, cudaMemcpyDeviceToHost, c->copyStream));
+                rc = deliver(c, pg, (int)k, dsrc, hdst + off, 1, cnt * 8, cnt * 8);
             } else {            // time-major into a wider block: n*24 bytes per epoch at a pitch of totalRows*24
-                AZ_CUDA(cudaMemcpy2DAsync(hdst + ((size_t)u0 * totalRows + rowOffset) * 3, (size_t)totalRows * 24, dsrc,
-                                          (size_t)n * 24, (size_t)n * 24, u1 - u0, cudaMemcpyDeviceToHost,
-                                          c->copyStream));
+                rc = deliver(c, pg, (int)k, dsrc, hdst + ((size_t)u0 * totalRows + rowOffset) * 3, u1 - u0, (size_t)n * 24,
+                             (size_t)totalRows * 24);
             }
+            if (rc != ASTROZ_OK) return rc;
         }
     }
     AZ_CUDA(cudaEventRecord(c->ev[5], s));  // ... to the last kernel of the last chunk
@@ -1057,9 +1247,39 @@ static int32_t propagate_host_queue(Constellation *c, const double *jd, const do
 static int32_t propagate_host_wait(Constellation *c) {
     if (!c->stream) return ASTROZ_OK;
     AZ_CUDA(cudaSetDevice(c->device));
+    const int32_t rr = run_ring(c);
+    if (rr != ASTROZ_OK) return rr;
     AZ_CUDA(cudaStreamSynchronize(c->copyStream));
     AZ_CUDA(cudaStreamSynchronize(c->stream));
     return ASTROZ_OK;
+}
+
+static int32_t wait_all(const std::vector<Constellation *> &hs) {
+    bool anyPlan = false;
+    for (Constellation *c : hs) anyPlan = anyPlan || !c->plan.empty();
+    int32_t first = ASTROZ_OK;
+    if (!anyPlan || hs.size() == 1) {
+        for (Constellation *c : hs) {
+            const int32_t rc = propagate_host_wait(c);
+            if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
+        }
+        return first;
+    }
+    std::vector<int32_t> rcs(hs.size(), ASTROZ_OK);
+    std::vector<std::string> errs(hs.size());
+    std::vector<std::thread> th;
+    for (size_t k = 0; k < hs.size(); ++k)
+        th.emplace_back([&, k] {
+            rcs[k] = propagate_host_wait(hs[k]);
+            if (rcs[k] != ASTROZ_OK) errs[k] = g_lastError;  // thread-local in the worker: carry it back
+        });
+    for (auto &t : th) t.join();
+    for (size_t k = 0; k < hs.size(); ++k)
+        if (rcs[k] != ASTROZ_OK && first == ASTROZ_OK) {
+            first = rcs[k];
+            g_lastError = errs[k];
+        }
+    return first;
 }
 
 int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const double *jd, const double *fr,
@@ -1080,10 +1300,8 @@ int32_t astroz_cuda_constellation_propagate(astroz_constellation_t h, const doub
         rc = propagate_host_queue(c->shards[k], jd, fr, n_times, pos, vel, mode, layout, c->shardRow0[k], c->cat.n);
         if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
     }
-    for (Constellation *sh : c->shards) {
-        rc = propagate_host_wait(sh);
-        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
-    }
+    rc = wait_all(c->shards);
+    if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
     return first;
 }
 
@@ -1254,12 +1472,16 @@ static int32_t sgp4_into_host_queue(Constellation *c, const double *times, uint3
     int32_t rc = sgp4_into_common(c, times, n_times, epoch_offsets, c->dPos.p, vel ? c->dVel.p : nullptr, mode,
                                   reference_jd, layout, s, 3, mask, ns);
     if (rc != ASTROZ_OK) return rc;
+    c->plan.clear();
+    AZ_CUDA(cudaEventRecord(c->chunkDone[0], s));
+    AZ_CUDA(cudaStreamWaitEvent(c->copyStream, c->chunkDone[0], 0));
     for (int which = 0; which < (vel ? 2 : 1); ++which) {
         double *dst = host_at(which ? vel : pos);
         const double *src = which ? c->dVel.p : c->dPos.p;
-        if (!strided) AZ_CUDA(cudaMemcpyAsync(dst, src, dense * 8, cudaMemcpyDeviceToHost, s));
-        else AZ_CUDA(cudaMemcpy2DAsync(dst, (size_t)rows * 24, src, (size_t)ns * 24, (size_t)ns * 24, n_times,
-                                       cudaMemcpyDeviceToHost, s));
+        const bool pg = is_pageable(which ? vel : pos);
+        if (!strided) rc = deliver(c, pg, 0, src, dst, 1, dense * 8, dense * 8);
+        else rc = deliver(c, pg, 0, src, dst, n_times, (size_t)ns * 24, (size_t)rows * 24);
+        if (rc != ASTROZ_OK) return rc;
     }
     return ASTROZ_OK;
 }
@@ -1282,8 +1504,7 @@ int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *
         rc = sgp4_into_host_queue(c, times, n_times, epoch_offsets, pos, vel, mode, reference_jd, layout, satellite_mask,
                                   rows, 0);
         if (rc != ASTROZ_OK) return rc;
-        AZ_CUDA(cudaStreamSynchronize(c->stream));
-        return ASTROZ_OK;
+        return propagate_host_wait(c);
     }
     int32_t first = ASTROZ_OK;
     for (size_t k = 0; k < c->shards.size(); ++k) {
@@ -1292,10 +1513,8 @@ int32_t astroz_cuda_sgp4_propagate_into(astroz_constellation_t h, const double *
                                   satellite_mask ? satellite_mask + near0 : nullptr, rows, near0);
         if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
     }
-    for (Constellation *sh : c->shards) {
-        rc = propagate_host_wait(sh);
-        if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
-    }
+    rc = wait_all(c->shards);
+    if (rc != ASTROZ_OK && first == ASTROZ_OK) first = rc;
     return first;
 }
 
@@ -1662,6 +1881,18 @@ int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3]
     std::memcpy(pos, r, 24);
     std::memcpy(vel, r + 3, 24);
     return rc;
+}
+
+// ---- caller-owned buffers: explicit page-locking ------------------------------------------------------------
+int32_t astroz_cuda_host_register(void *p, size_t bytes) {
+    if (!p) return ASTROZ_NULL_POINTER;
+    AZ_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return ASTROZ_OK;
+}
+int32_t astroz_cuda_host_unregister(void *p) {
+    if (!p) return ASTROZ_NULL_POINTER;
+    AZ_CUDA(cudaHostUnregister(p));
+    return ASTROZ_OK;
 }
 
 // ---- multi-device handles --------------------------------------------------------------------------------

@@ -74,6 +74,14 @@ const char *astroz_cuda_last_error(void);
 /* pinned host buffers for zero-staging device<->host copies of the output block */
 void *astroz_cuda_host_alloc(size_t bytes);
 void astroz_cuda_host_free(void *p);
+/* Caller-owned buffers.  The host-buffer calls accept ANY host memory.  A buffer from astroz_cuda_host_alloc, or
+ * one page-locked with astroz_cuda_host_register (cudaHostRegister: costs about as much as touching the pages once,
+ * so it pays for blocks that are reused), receives the result by direct DMA.  Plain pageable memory (a numpy array, a
+ * Zig slice from the page allocator) is served through a ring of pinned slots inside the handle: the result leaves the
+ * GPU in 8 MB pieces at the full PCIe rate and a small pool of host threads (ASTROZ_COPY_THREADS, default 8) copies
+ * each landed piece to its place while the next ones are in flight. */
+int32_t astroz_cuda_host_register(void *p, size_t bytes);
+int32_t astroz_cuda_host_unregister(void *p);
 
 /* ------------------------------------------------------------------------------------------------
  * Constellation: replaces Constellation.init / propagate / resetCarry / deinit

@@ -987,3 +987,35 @@ def test_multi_device_handle_device_count_knob(az, synth, monkeypatch):
     assert np.array_equal(c.propagate(jd, fr)[0], c2.propagate(jd, fr)[0])
     with pytest.raises(az.AstrozCudaError):
         az.Constellation(tles, device=-2)
+
+
+def test_caller_owned_pageable_and_registered_buffers(az, synth):
+    """The reference writes into whatever slices the caller passes (src/Constellation.zig:245-258; numpy buffers from
+    Python, bindings/python/src/satrec.zig:917-942).  Pageable destinations are served through the handle's pinned
+    ring + host copy pool, page-locked ones by direct DMA: all three routes must give the same bytes, for blocks that
+    span several ring pieces, both layouts, and the strided (wider block) form."""
+    tles = synth.near_earth_catalog(900)
+    jd, fr = synth.time_grid(1440)
+    c = az.Constellation(tles)
+    n, nt = 900, 1440                                   # 31 MB per array: four 8 MB ring pieces
+    for layout in (az.Layout.satelliteMajor, az.Layout.timeMajor):
+        ref_p, ref_v = c.propagate(jd, fr, layout=layout)                     # pinned (the wrapper's own allocation)
+        shape = ref_p.shape
+        pg_p, pg_v = np.full(shape, -1.0), np.full(shape, -1.0)              # pageable
+        c.propagate(jd, fr, pg_p, pg_v, layout=layout)
+        assert np.array_equal(pg_p, ref_p) and np.array_equal(pg_v, ref_v)
+        rg_p = np.full(shape, -2.0)                                           # page-locked in place by the caller
+        az.host_register(rg_p)
+        try:
+            c.propagate(jd, fr, rg_p, None, layout=layout, velocities=False)
+        finally:
+            az.host_unregister(rg_p)
+        assert np.array_equal(rg_p, ref_p)
+    # stateless path into a wider pageable block: rows beyond the constellation and the pitch gaps stay untouched
+    times = np.arange(0.0, 1440.0, 1.0)
+    off = (2460437.5 - c.epochs) * 1440.0
+    want_p, want_v = c.propagate_into(times, epoch_offsets=off, time_major=True)
+    wide_p, wide_v = np.full((nt, n + 7, 3), 5.0), np.full((nt, n + 7, 3), 5.0)
+    c.propagate_into(times, wide_p, wide_v, epoch_offsets=off, time_major=True, output_stride=n + 7)
+    assert np.array_equal(wide_p[:, :n], want_p) and np.array_equal(wide_v[:, :n], want_v)
+    assert np.all(wide_p[:, n:] == 5.0) and np.all(wide_v[:, n:] == 5.0)
