@@ -101,10 +101,28 @@ def test_synthetic_catalog_is_valid(oracle):
     assert np.bincount(k2, minlength=4).tolist() == [320, 20, 40, 20]
 
 
-def test_integration_doc_binds_every_export():
-    """INTEGRATION.md shows the reference-side (Zig) extern declaration of every symbol the header declares."""
+def test_zig_bindings_cover_every_export():
+    """zig/src/c_api/cuda.zig (the reference-side binding a maintainer copies to src/c_api/cuda.zig) is generated from
+    the header and committed: it must be up to date and declare every exported symbol with the header's arity; the
+    device branch of Constellation.zig (zig/src/Constellation.device.zig) may only call symbols that exist."""
+    import sys
+
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_zig_bindings.py"), "--check"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
     header = open(os.path.join(ROOT, "include", "astroz_b200.h")).read()
     declared = set(re.findall(r"\b(astroz_cuda_[a-z0-9_]+)\s*\(", header))
+    zig = open(os.path.join(ROOT, "zig", "src", "c_api", "cuda.zig")).read()
+    bound = dict(re.findall(r"pub extern fn (astroz_cuda_[a-z0-9_]+)\(([^)]*)\)", zig))
+    assert set(bound) == declared, sorted(declared ^ set(bound))
+    stripped = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    for name, zargs in bound.items():
+        cargs = re.search(r"\b" + name + r"\s*\(([^;{]*?)\)\s*;", stripped, flags=re.S).group(1).strip()
+        n_c = 0 if cargs in ("", "void") else cargs.count(",") + 1
+        n_z = len(re.findall(r"(?:^|, )\w+: ", zargs))
+        assert n_c == n_z, (name, n_c, n_z)
+    branch = open(os.path.join(ROOT, "zig", "src", "Constellation.device.zig")).read()
+    used = set(re.findall(r"cuda\.(astroz_cuda_[a-z0-9_]+)\(", branch))
+    assert used and used <= declared, sorted(used - declared)
     doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
-    bound = set(re.findall(r"pub extern fn (astroz_cuda_[a-z0-9_]+)\(", doc))
-    assert bound == declared, sorted(declared ^ bound)
+    assert "zig/src/c_api/cuda.zig" in doc and "zig/src/Constellation.device.zig" in doc
