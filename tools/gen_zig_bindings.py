@@ -78,7 +78,7 @@ def render() -> str:
         "",
     ]
     for ret, name, args in declarations(HEADER):
-        zargs = ", ".join(f"{re.sub(r'\\[\\d+\\]$', '', n)}: {zig_type(t, n)}" for t, n in args)
+        zargs = ", ".join(f"{n.split('[')[0]}: {zig_type(t, n)}" for t, n in args)
         out.append(f"pub extern fn {name}({zargs}) {RET[ret]};")
     out += [
         "",

@@ -37,13 +37,13 @@ pub extern fn astroz_cuda_sgp4_screen(h: Handle, times: ?[*]const f64, n_times: 
 pub extern fn astroz_cuda_constellation_coarse_screen_device(h: Handle, d_positions: ?[*]const f64, num_sats: u32, num_times: u32, layout: i32, threshold: f64, d_valid_mask: ?[*]const u8, d_pairs: ?[*]u32, d_t_indices: ?[*]u32, max_results: u32, count: *u64) i32;
 pub extern fn astroz_cuda_sgp4_screen_all(h: Handle, times: ?[*]const f64, n_times: u32, epoch_offsets: ?[*]const f64, threshold: f64, pairs: ?[*]u32, t_indices: ?[*]u32, max_results: u32, count: *u64) i32;
 pub extern fn astroz_cuda_constellation_synchronize(h: Handle) i32;
-pub extern fn astroz_cuda_constellation_last_kernel_ms(h: Handle, ms[3]: *[3]f32) i32;
+pub extern fn astroz_cuda_constellation_last_kernel_ms(h: Handle, ms: *[3]f32) i32;
 pub extern fn astroz_cuda_sgp4_init(line1: [*:0]const u8, line2: [*:0]const u8, grav: i32, device: i32, out: *Handle) i32;
 pub extern fn astroz_cuda_sgp4_free(h: Handle) void;
 pub extern fn astroz_cuda_sgp4_is_deep_space(h: Handle) i32;
 pub extern fn astroz_cuda_sgp4_epoch(h: Handle, epoch_jd: ?[*]f64) i32;
 pub extern fn astroz_cuda_sgp4_elements(h: Handle, out10: ?[*]f64) i32;
-pub extern fn astroz_cuda_sgp4_propagate(h: Handle, tsince: f64, pos[3]: *[3]f64, vel[3]: *[3]f64) i32;
+pub extern fn astroz_cuda_sgp4_propagate(h: Handle, tsince: f64, pos: *[3]f64, vel: *[3]f64) i32;
 pub extern fn astroz_cuda_sgp4_propagate_batch(h: Handle, times: ?[*]const f64, results: ?[*]f64, count: u32) i32;
 pub extern fn astroz_cuda_sgp4_array(h: Handle, jd: ?[*]const f64, fr: ?[*]const f64, epoch_jd: f64, results: ?[*]f64, count: u32) i32;
 pub extern fn astroz_cuda_constellation_propagate_device_f32(h: Handle, jd: ?[*]const f64, fr: ?[*]const f64, n_times: u32, d_pos: ?[*]f64, d_vel: ?[*]f64, phase64: i32, stream: ?*anyopaque) i32;
