@@ -251,6 +251,14 @@ class Harness:
         self.stream = torch.cuda.Stream(self.dev)   # kernels, events and the collective all go through this stream
         torch.cuda.set_stream(self.stream)
 
+    @classmethod
+    def solo(cls, other: "Harness") -> "Harness":
+        """The same device and stream, without the collectives: for a leg only one rank runs."""
+        me = cls.__new__(cls)
+        me.__dict__.update(other.__dict__)
+        me.dist = None
+        return me
+
     def barrier(self):
         self.torch.cuda.synchronize(self.dev)
         if self.dist is not None:
@@ -340,6 +348,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         raise SystemExit("bench.py needs a CUDA device: astroz_b200 has no CPU propagation path")
     h = Harness(rank, local_rank, world)
     dev, stream, dist = h.dev, h.stream, h.dist
+    affinity0 = os.sched_getaffinity(0) if world > 1 else None
     numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None   # host staging next to this GPU's PCIe root
 
     tles, jd, fr, desc = workload(args.workload)
@@ -409,6 +418,26 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     legs["ecef_positions_only"] = e2e_leg(h, c, jd, fr, n_local, 1, 1, False, True, e2e_steps, cells,
                                           "astroz.propagate() default: ECEF, velocities=False, time-major "
                                           "(bindings/python/astroz/__init__.py:411-413)")
+
+    # ---- N > 1: the same job through ONE handle in ONE process (device = -1: the library fans the call out over the
+    # GPUs, each copying its rows over its own PCIe link into one host block).  Rank 0 runs it, the other ranks wait.
+    if world > 1:
+        h.barrier()
+        if rank == 0:
+            try:
+                if affinity0 is not None:
+                    os.sched_setaffinity(0, affinity0)      # the single process serves every GPU: no NUMA pinning
+                os.environ["ASTROZ_DEVICES"] = str(world)
+                multi = Constellation(tles, device=-1)
+                ids, first_rows = multi.devices
+                leg = e2e_leg(Harness.solo(h), multi, jd, fr, n, 0, 0, True, True, e2e_steps, cells,
+                              f"ONE Constellation handle over {len(ids)} GPUs (device = -1), one process, one propagate call")
+                leg["devices"] = ids
+                legs["single_handle_all_gpus"] = leg
+                del multi
+            except Exception as exc:
+                legs["single_handle_all_gpus"] = {"unavailable": repr(exc)[:300]}
+        h.barrier()
 
     # ---- a device-resident consumer: fused propagate + single-target screen through the host API (N = 1) ----------
     screen = None
