@@ -255,15 +255,21 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
             small &= !abs_gt(tho[k], kHiTiny);
             micro &= !abs_gt(tho[k], kHiMicro);
         }
+        // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle (1e-6 .. 1e-3 rad over days for catalogued objects),
+        // rotate instead of a second reduction, with the shortest series that covers it.  The choice is made once for
+        // the thread's lanes, outside the lane loops, so each alternative is straight-line code over all lanes.
+        double sd[kN], cd[kN];
+        if (micro) {
+            AZ_LANES sincos_micro(tho[k], sd[k], cd[k]);
+        } else if (small) {
+            AZ_LANES sincos_tiny(tho[k], sd[k], cd[k]);
+        } else if (!big) {
+            AZ_LANES sincos_quarter(tho[k], sd[k], cd[k]);
+        } else {
+            AZ_LANES sincos_full(tho[k], sd[k], cd[k]);
+        }
         AZ_LANES {
-            // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle (1e-6 .. 1e-3 rad over days for catalogued objects),
-            // rotate instead of a second reduction, with the shortest series that covers it
-            double sd, cd;
-            if (micro) sincos_micro(tho[k], sd, cd);
-            else if (small) sincos_tiny(tho[k], sd, cd);
-            else if (!big) sincos_quarter(tho[k], sd, cd);
-            else sincos_full(tho[k], sd, cd);
-            const double sinmm = fma(sm[k], cd, cm[k] * sd);
+            const double sinmm = fma(sm[k], cd[k], cm[k] * sd[k]);
             const double t3 = t2[k] * t[k];
             const double t4 = t3 * t[k];
             tempa[k] = tempa[k] - d2 * t2[k] - d3 * t3 - d4 * t4;

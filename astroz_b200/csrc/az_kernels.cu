@@ -423,6 +423,22 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 #endif
 #define AZ_COMPACT_K1 4, 256, 3, 2
 
+// The launch shape (epochs per thread) follows the time axis, identically for the local and the fused all-gather store
+// stages, so a cell is computed by the same instruction stream -- and to the same bits -- whichever way it leaves the SM.
+template <int kLayout, int kMode, bool kVel, int kGather>
+static cudaError_t launch_k1_shaped(const GridArgs &a, cudaStream_t stream) {
+    if constexpr (kLayout == 1 || kMode == 2) {
+        return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1, kGather>(a, stream);
+    } else {
+        // a thread's epochs are 32 apart: short or ragged time axes pad up to 32 * lanes, so take the widest shape
+        // that does not add padded warp-runs (16 epochs x 10^6 Monte-Carlo draws: one lane, not three)
+        const uint32_t runs1 = (a.nTimes + 31) / 32, runs2 = (a.nTimes + 63) / 64 * 2, runs3 = (a.nTimes + 95) / 96 * 3;
+        if (runs3 <= runs2 && runs3 <= runs1) return launch_k1<kLayout, kMode, kVel, AZ_DEFAULT_K1, kGather>(a, stream);
+        if (runs2 <= runs1) return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1, kGather>(a, stream);
+        return launch_k1<kLayout, kMode, kVel, 4, 256, 4, 1, kGather>(a, stream);
+    }
+}
+
 template <int kLayout, int kMode, bool kVel>
 static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int variant) {
 #ifdef AZ_TUNING
@@ -457,25 +473,15 @@ static cudaError_t launch_k1_variant(const GridArgs &a, cudaStream_t stream, int
 #else
     (void)variant;
 #endif
-    if constexpr (kLayout == 1 || kMode == 2) {
-        return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1>(a, stream);
-    } else {
-        // a thread's epochs are 32 apart: short or ragged time axes pad up to 32 * lanes, so take the widest shape
-        // that does not add padded warp-runs (16 epochs x 10^6 Monte-Carlo draws: one lane, not three)
-        const uint32_t runs1 = (a.nTimes + 31) / 32, runs2 = (a.nTimes + 63) / 64 * 2, runs3 = (a.nTimes + 95) / 96 * 3;
-        if (runs3 <= runs2 && runs3 <= runs1) return launch_k1<kLayout, kMode, kVel, AZ_DEFAULT_K1>(a, stream);
-        if (runs2 <= runs1) return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1>(a, stream);
-        return launch_k1<kLayout, kMode, kVel, 4, 256, 4, 1>(a, stream);
-    }
+    return launch_k1_shaped<kLayout, kMode, kVel, 0>(a, stream);
 }
 
 cudaError_t launch_sgp4_grid(const GridArgs &a, int mode, int layout, cudaStream_t stream, int variant) {
     if (a.gather != 0) {  // fused all-gather: satellite-major TEME only
         if (layout != 0 || mode != 0) return cudaErrorInvalidValue;
         const bool gv = (a.gather == 1 ? a.mcVel : a.peerVel[0]) != nullptr;
-        if (a.gather == 1) return gv ? launch_k1<0, 0, true, AZ_DEFAULT_K1, 1>(a, stream)
-                                     : launch_k1<0, 0, false, AZ_DEFAULT_K1, 1>(a, stream);
-        return gv ? launch_k1<0, 0, true, AZ_DEFAULT_K1, 2>(a, stream) : launch_k1<0, 0, false, AZ_DEFAULT_K1, 2>(a, stream);
+        if (a.gather == 1) return gv ? launch_k1_shaped<0, 0, true, 1>(a, stream) : launch_k1_shaped<0, 0, false, 1>(a, stream);
+        return gv ? launch_k1_shaped<0, 0, true, 2>(a, stream) : launch_k1_shaped<0, 0, false, 2>(a, stream);
     }
     const bool vel = a.vel != nullptr;
     if (a.nSats == 1 && a.nTimes >= 64 && a.mask == nullptr) {  // single satellite: spread the time axis over the whole GPU

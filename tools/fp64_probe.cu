@@ -9,10 +9,15 @@
 //   5 add_2   DADD x, x, y_k                                    2 fresh pairs
 //   6 fma_ur  DFMA x, x, UR, Rb.reuse  (kernel parameter)       1 fresh pair
 //   7 mix     the K1 mix: per 8 instr 3 fma_3, 2 fma_2, 3 mul_2
+//   8 fma+1i  one independent integer instruction (IMAD) per DFMA: does the integer op hide behind the DFMA's two
+//   9 fma+2i  pipe cycles, or does every issued instruction cost an issue cycle of its own?
 // `chains` independent accumulators per thread (ILP), `warps` per SM (TLP): chains=1 & 4 warps/SM exposes the latency.
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o gpurun_out/fp64_probe tools/fp64_probe.cu
 #include <cstdio>
 #include <cuda_runtime.h>
+
+static double *g_d, *g_in;
+static int g_sms;
 
 template <int kPat, int kChains>
 __global__ void __launch_bounds__(256) probe(double *out, const double *in, int iters, double a) {
@@ -55,8 +60,56 @@ __global__ void __launch_bounds__(256) probe(double *out, const double *in, int 
     if (s == 1234.5678) out[0] = s;
 }
 
-static double *g_d, *g_in;
-static int g_sms;
+template <int kInts>
+__global__ void __launch_bounds__(256) probe_int(double *out, const double *in, int iters, int m) {
+    double x[8];
+    int q[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        x[k] = threadIdx.x * 1e-9 + k;
+        q[k] = threadIdx.x + k;
+    }
+    double ra = in[16] + threadIdx.x * 1e-13;
+    asm volatile("" : "+d"(ra));
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                x[k] = fma(x[k], ra, 0.5);
+                if (kInts >= 1) q[k] = q[k] * m + 12345;         // IMAD
+                if (kInts >= 2) q[(k + 4) & 7] ^= (q[k] >> 3);    // SHF/LOP3
+            }
+        }
+    }
+    double s = 0;
+    int t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s += x[k]; t += q[k]; }
+    if (s == 1234.5678 || t == 123456789) out[0] = s + t;
+}
+
+template <int kInts>
+double run_int() {
+    const int threads = 256, blocks = g_sms * 8, iters = 2048;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        probe_int<kInts><<<blocks, threads>>>(g_d, g_in, iters, 3);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 1 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 64.0 * iters * (double)blocks * threads / (best * 1e-3);  // DFMAs per second
+}
 
 template <int kPat, int kChains>
 double run(int warpsPerSm) {
@@ -113,5 +166,10 @@ int main() {
     row<4>("mul x,y_k (2 fresh pairs)", clk);
     row<5>("add x,y_k (2 fresh pairs)", clk);
     row<7>("K1 mix 3:2:3 fma3:fma2:mul2", clk);
+    {
+        auto cyc = [&](double ips) { return g_sms * 4.0 * clk / (ips / 32.0); };
+        printf("{\"pattern\": \"DFMA alone / +1 integer instr / +2-3 integer instrs, per DFMA\", \"cycles_per_dfma\": [%.3f, %.3f, %.3f]}\n",
+               cyc(run_int<0>()), cyc(run_int<1>()), cyc(run_int<2>()));
+    }
     return 0;
 }
