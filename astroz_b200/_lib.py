@@ -11,7 +11,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libastroz_b200.so")
+# ASTROZ_B200_LIB points measurement tools at an alternative build of the SAME library (tools/variant_sweep.sh);
+# there is no other implementation to fall back to
+LIB_PATH = os.environ.get("ASTROZ_B200_LIB") or os.path.join(_HERE, "libastroz_b200.so")
 
 OK = 0
 ERROR_NAMES = {

@@ -64,8 +64,10 @@ int32_t status_to_code(int st) {  // kernel-level code -> C API code (src/c_api/
 // staged by the driver through a small internal buffer, synchronously, at a fraction of the PCIe rate.  Instead the
 // result leaves the GPU in pieces into a ring of pinned slots owned by the handle (full-rate DMA), and a small pool of
 // host threads copies each landed piece to its final place while the next pieces are in flight.
-constexpr size_t kPieceBytes = 8u << 20;
-constexpr int kRingSlots = 4;
+// Piece size: large enough that (a) the wake-up of the copy threads is amortised and (b) each thread's share (a few MB)
+// is above libc's non-temporal threshold, so the destination lines are streamed instead of read for ownership first.
+constexpr size_t kPieceBytes = 32u << 20;
+constexpr int kRingSlots = 3;
 
 class CopyPool {  // process-wide, created on first use, never destroyed (workers sleep on the condition variable)
 public:
@@ -77,7 +79,7 @@ public:
     // copy `rows` rows of rowBytes from a contiguous source to a destination with pitch hpitch, split over the pool
     void copy(char *dst, const char *src, size_t rows, size_t rowBytes, size_t hpitch) {
         const size_t total = rows * rowBytes;
-        const int parts = (int)std::max<size_t>(1, std::min<size_t>(workers_.size(), total / (256u << 10)));
+        const int parts = (int)std::max<size_t>(1, std::min<size_t>(workers_.size(), total / (1u << 20)));
         if (parts <= 1 || workers_.empty()) {
             run(dst, src, 0, rows, rowBytes, hpitch, 0, total);
             return;

@@ -538,7 +538,10 @@ cudaError_t launch_sdp4_lattice(const Sdp4Sat *sats, uint32_t nSats, double2 *la
 constexpr int kSdp4Threads = 128;
 constexpr int kSdp4Stripe = 512;
 
-constexpr int kSdp4Lanes = 2;  // epochs per thread, 32 apart (each warp-run is 32 consecutive epochs, like K1)
+#ifndef AZ_K2_LANES
+#define AZ_K2_LANES 2
+#endif
+constexpr int kSdp4Lanes = AZ_K2_LANES;  // epochs per thread, 32 apart (each warp-run is 32 consecutive epochs, like K1)
 
 template <int kLayout, int kMode, bool kVel, int kGather, int kMinBlocks>
 __global__ void __launch_bounds__(kSdp4Threads, kMinBlocks) sdp4_grid_kernel(const GridArgs a) {

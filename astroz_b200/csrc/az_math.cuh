@@ -87,6 +87,24 @@ constexpr double kTwoPi = 6.28318530717958647692528676655900577;
 // constant-bank operands (c[bank][offset]) for free, whereas an immediate costs two UMOV / IMAD.MOV issue
 // slots each time it is materialised -- ncu showed ~230 of 739 instructions per cell were exactly that
 // (profiles/r01_sgp4_grid_notes.md), making the kernel issue-bound instead of fp64-pipe-bound.
+// sin / cos kernels on |r| <= pi/4 (tools/fit_sincos_imm.py): sin r = r + r^3 (s1 + s2 z + ... + s6 z^5),
+// cos r = 1 - z/2 + z^2 (c1 + ... + c6 z^5), z = r^2.  The three highest coefficients of each are fp64 numbers whose low
+// 32 bits are zero -- sm_100 encodes such an operand in the instruction, so the Horner step that uses it reads two
+// register pairs instead of three (a DFMA with three fresh register-pair sources holds the fp64 pipe 3 cycles instead
+// of 2, tools/fp64_probe.cu) -- and the three lowest were re-solved with those fixed: max error 3.5e-16 (sin),
+// 4.2e-17 (cos) in exact arithmetic, the same class as the unconstrained fdlibm minimax set (6e-18 / 5e-19 before the
+// ~1e-16 of rounding both carry).
+#define AZ_S4 0x1.71de3p-19
+#define AZ_S5 -0x1.ae5dbp-26
+#define AZ_S6 0x1.5d61ep-33
+#define AZ_C4 -0x1.27e4fp-22
+#define AZ_C5 0x1.1ee9ep-29
+#define AZ_C6 -0x1.8faaep-37
+// pi/2 = kPio2A (21 significant bits: k * kPio2A is exact for |k| < 2^32) + kPio2B (the next 53 bits); the third part,
+// 1.06e-23, is below 1e-17 for every |x| < 1e6
+#define AZ_PIO2A 0x1.921fbp+0
+#define AZ_PIO2B 0x1.5110b4611a626p-22
+
 struct MathTable {
     double s1, s2, s3, s4, s5, s6;          // fdlibm __kernel_sin
     double c1, c2, c3, c4, c5, c6;          // fdlibm __kernel_cos
@@ -96,11 +114,11 @@ struct MathTable {
 };
 #define AZ_MATH_TABLE_INIT                                                                                    \
     {                                                                                                         \
-        -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,                 \
-            2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10,              \
-            4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,              \
-            -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11,             \
-            6.36619772367581382433e-01, 1.57079632679489655800e+00, 6.12323399573676603587e-17,               \
+        -0x1.55555555550eap-3, 0x1.11111110eaa94p-7, -0x1.a01a018403eabp-13,                                  \
+            AZ_S4, AZ_S5, AZ_S6,                                                                              \
+            0x1.5555555555088p-5, -0x1.6c16c16bccf0cp-10, 0x1.a01a0172105bep-16,                              \
+            AZ_C4, AZ_C5, AZ_C6,                                                                              \
+            6.36619772367581382433e-01, AZ_PIO2A, AZ_PIO2B,                                                  \
             -1.49738490485916983692e-33, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 24.0, -1.0 / 720.0,    \
             1.0 / 40320.0, 0.78, 0.05, 0.95, 1.0e-6, 2.0e-15, 1.0 / 6.28318530717958647692528676655900577,    \
             6.28318530717958647692528676655900577, 3.14159265358979323846264338327950288, 2.0e-3, 1.0e-8      \
@@ -175,16 +193,16 @@ AZ_HD double sqrt_(double x) { return sqrt_from_rsqrt(x, rsqrt_nr(x)); }
 // ---- sin / cos --------------------------------------------------------------------------------
 // fdlibm __kernel_sin / __kernel_cos coefficients (public domain, Sun Microsystems), |r| <= pi/4.
 AZ_HD double ksin(double r, double r2) {
-    double p = fma(r2, AZK(s6), AZK(s5));
-    p = fma(p, r2, AZK(s4));
+    double p = fma(r2, AZ_S6, AZK(s5));  // s6, s4 (c6, c4 below) are immediates; s5 / c5 ride in a register as the addend
+    p = fma(p, r2, AZ_S4);
     p = fma(p, r2, AZK(s3));
     p = fma(p, r2, AZK(s2));
     p = fma(p, r2, AZK(s1));
     return fma(p, r2 * r, r);
 }
 AZ_HD double kcos(double r2) {
-    double p = fma(r2, AZK(c6), AZK(c5));
-    p = fma(p, r2, AZK(c4));
+    double p = fma(r2, AZ_C6, AZK(c5));
+    p = fma(p, r2, AZ_C4);
     p = fma(p, r2, AZK(c3));
     p = fma(p, r2, AZK(c2));
     p = fma(p, r2, AZK(c1));
@@ -198,8 +216,8 @@ AZ_HD void sincos_full(double x, double &s, double &c) {
     double kf = fma(x, AZK(twoOverPi), kMagic);
     const unsigned q = (unsigned)dbl_lo(kf);
     kf -= kMagic;
-    double r = fma(-kf, AZK(pio2Hi), x);
-    r = fma(-kf, AZK(pio2Mid), r);  // third part of pi/2 (-1.5e-33 * k) is < 1e-17 for every |x| < 1e15
+    double r = fma(-kf, AZ_PIO2A, x);  // exact product (21-bit constant), one rounding
+    r = fma(-kf, AZK(pio2Mid), r);     // pio2Mid = AZ_PIO2B
     double r2 = r * r;
     double sr = ksin(r, r2);
     double cr = kcos(r2);
@@ -232,8 +250,10 @@ AZ_HD void sincos_tiny(double x, double &s, double &c) {
 
 // |x| <= 2e-3 (the J2 short-period angles of any orbit above the surface are < 1e-3): abs error < 3e-16 |x|
 AZ_HD void sincos_micro(double x, double &s, double &c) {
+    // -1/6 and 1/24 rounded to 21 significant bits (immediate operands): the rounding moves sin by |x|^3 * 4e-8 <= 3e-16
+    // and cos by x^4 * 1e-8 <= 2e-19 on this range
     double x2 = x * x;
-    s = fma(x * x2, AZK(ts3), x);
+    s = fma(x * x2, -0x1.55555p-3, x);
     c = fma(x2, fma(x2, AZK(tc4), -0.5), 1.0);
 }
 

@@ -1,0 +1,104 @@
+#!/usr/bin/env python
+"""Design of the sin/cos kernels whose high-order coefficients are fp64 numbers with a zero low word (CPU tool).
+
+On sm_100 a DFMA that reads three fresh 64-bit register pairs occupies the fp64 pipe for 3 cycles instead of 2
+(tools/fp64_probe.cu), and ptxas keeps polynomial coefficients in registers, so a Horner step fma(p, z, c) with c in a
+register is such an instruction.  An fp64 operand whose low 32 bits are zero is encoded in the instruction as an
+immediate and costs no register read.  This script re-fits the |r| <= pi/4 kernels
+    sin r = r + r^3 (s1 + s2 z + ... + s6 z^5),   cos r = 1 - z/2 + z^2 (c1 + c2 z + ... + c6 z^5),   z = r^2
+with the trailing coefficients constrained to 21 significant bits: the coefficients are rounded one at a time from the
+highest order down, and after each rounding the remaining (full-precision) ones are re-solved by weighted least squares
+on Chebyshev nodes, so they absorb most of the perturbation.  Prints the coefficient tables and the maximum error.
+    python tools/fit_sincos_imm.py [n_imm_sin] [n_imm_cos]
+"""
+import struct
+import sys
+
+import mpmath as mp
+
+mp.mp.dps = 60
+PIO4 = mp.pi / 4 * (1 + mp.mpf(2) ** -20)   # a little beyond pi/4: the Cody-Waite reduction lands within half a ulp of it
+
+
+def imm(x):
+    """nearest double whose low 32 bits are zero"""
+    b = struct.unpack("<Q", struct.pack("<d", float(x)))[0]
+    lo = b & 0xffffffff
+    b -= lo
+    if lo >= 0x80000000:
+        b += 1 << 32
+    return mp.mpf(struct.unpack("<d", struct.pack("<Q", b))[0])
+
+
+def dbl(x):
+    return mp.mpf(float(x))
+
+
+def nodes(n):
+    return [PIO4 * mp.cos(mp.pi * (2 * k + 1) / (2 * n)) for k in range(n)]
+
+
+def fit(target, n_coef, n_imm, weight):
+    """coefficients c[0..n_coef) of sum c_k z^k ~ target(z), the last n_imm of them immediates"""
+    rs = [r for r in nodes(160) if r > 0]
+    zs = [r * r for r in rs]
+    fixed = {}
+    for step in range(n_imm + 1):
+        free = [k for k in range(n_coef) if k not in fixed]
+        A = mp.matrix(len(zs), len(free))
+        b = mp.matrix(len(zs), 1)
+        for i, (r, z) in enumerate(zip(rs, zs)):
+            w = weight(r)
+            for j, k in enumerate(free):
+                A[i, j] = w * z ** k
+            b[i] = w * (target(r) - sum(fixed[k] * z ** k for k in fixed))
+        sol = mp.lu_solve(A.T * A, A.T * b)
+        coef = dict(fixed)
+        for j, k in enumerate(free):
+            coef[k] = sol[j]
+        if step == n_imm:
+            break
+        k = max(free)
+        fixed[k] = imm(coef[k])
+    out = [dbl(coef[k]) if k not in fixed else fixed[k] for k in range(n_coef)]
+    return out, sorted(fixed)
+
+
+def max_err(f, g, n=4001):
+    worst = mp.mpf(0)
+    for i in range(n):
+        r = PIO4 * (mp.mpf(2 * i) / (n - 1) - 1)
+        worst = max(worst, abs(f(r) - g(r)))
+    return worst
+
+
+def main():
+    n_is = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    n_ic = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+    s, s_imm = fit(lambda r: (mp.sin(r) - r) / r ** 3, 6, n_is, lambda r: r ** 3)
+    c, c_imm = fit(lambda r: (mp.cos(r) - 1 + r * r / 2) / r ** 4, 6, n_ic, lambda r: r ** 4)
+
+    def psin(r):
+        z = r * r
+        p = s[5]
+        for k in (4, 3, 2, 1, 0):
+            p = p * z + s[k]
+        return r + r ** 3 * p
+
+    def pcos(r):
+        z = r * r
+        p = c[5]
+        for k in (4, 3, 2, 1, 0):
+            p = p * z + c[k]
+        return 1 - z / 2 + z * z * p
+
+    print("sin: immediates at orders", [k + 1 for k in s_imm], " max |err| (exact arithmetic) =", mp.nstr(max_err(mp.sin, psin), 4))
+    for k, v in enumerate(s):
+        print(f"  s{k + 1} = {float(v)!r}   {float(v).hex()}")
+    print("cos: immediates at orders", [k + 1 for k in c_imm], " max |err| (exact arithmetic) =", mp.nstr(max_err(mp.cos, pcos), 4))
+    for k, v in enumerate(c):
+        print(f"  c{k + 1} = {float(v)!r}   {float(v).hex()}")
+
+
+if __name__ == "__main__":
+    main()
