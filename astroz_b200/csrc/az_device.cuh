@@ -67,15 +67,17 @@ struct SatAngles {  // inclination-dependent per-satellite (SGP4) or per-cell (S
 template <int kN>
 AZ_HD void rotate_small_n(const double (&s0)[kN], const double (&c0)[kN], const double (&d)[kN], double (&s)[kN],
                           double (&c)[kN]) {
+    // The micro series is evaluated unconditionally, as straight-line code the scheduler can interleave with its
+    // surroundings; the general evaluation overwrites it in a cold branch (never taken for physical orbits) that keeps
+    // the identity exact.
     bool big = false;
-    AZ_LANES big |= abs_gt(d[k], kHiMicro);
-    if (!big) {
-        AZ_LANES {
-            double sd, cd;
-            sincos_micro(d[k], sd, cd);
-            rotate(s0[k], c0[k], sd, cd, s[k], c[k]);
-        }
-    } else {  // never taken for physical orbits; keeps the identity exact
+    AZ_LANES {
+        double sd, cd;
+        sincos_micro(d[k], sd, cd);
+        rotate(s0[k], c0[k], sd, cd, s[k], c[k]);
+        big |= abs_gt(d[k], kHiMicro);
+    }
+    if (big) {
         AZ_LANES {
             double sd, cd;
             sincos_full(d[k], sd, cd);
@@ -102,6 +104,39 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
         sincos_full(u, s[k], c[k]);
         eps[k] = 0.0;
     }
+    // Hot path, straight-line: for an orbit with e below ~2e-3 (most of any catalog) Newton's first step is a "micro"
+    // rotation (|delta| <= 2e-3) and the second is below 1e-8 rad, where the first-order update is exact to 5e-17 and
+    // the solve is finished.  Both steps are evaluated speculatively, without the loop's control flow, so the scheduler
+    // interleaves them with the prologue and the short-period block; the flags are checked once, and any other orbit
+    // (or a lane that needs the +-0.95 clamp) runs the general loop below from the same starting point instead.
+    bool spec = true;
+    double s2[kN], c2[kN];
+    {
+        double d1[kN], s1[kN], c1[kN];
+        AZ_LANES {
+            const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
+            const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
+            d1[k] = esine * rcp_fast(1.0 - ecose);
+            spec &= !abs_gt(d1[k], kHiMicro);
+            double sd, cd;
+            sincos_micro(d1[k], sd, cd);
+            rotate(s[k], c[k], sd, cd, s1[k], c1[k]);
+        }
+        AZ_LANES {
+            const double esine = fma(axnl[k], s1[k], -(aynl[k] * c1[k]));
+            const double ecose = fma(axnl[k], c1[k], aynl[k] * s1[k]);
+            const double d = (esine - d1[k]) * rcp_fast(1.0 - ecose);
+            spec &= abs_lt(d, kHiLinear);
+            s2[k] = fma(c1[k], d, s1[k]);
+            c2[k] = fma(-s1[k], d, c1[k]);
+        }
+    }
+    if (spec) {
+        AZ_LANES {
+            s[k] = s2[k];
+            c[k] = c2[k];
+        }
+    } else
 #pragma unroll 1
     for (int it = 0; it < 10; ++it) {  // src/Sgp4.zig:687-694
         double delta[kN];
@@ -257,16 +292,17 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
         }
         // sin(mm) = sin(xmdf + tho): tho is a drag-sized angle (1e-6 .. 1e-3 rad over days for catalogued objects),
         // rotate instead of a second reduction, with the shortest series that covers it.  The choice is made once for
-        // the thread's lanes, outside the lane loops, so each alternative is straight-line code over all lanes.
+        // the thread's lanes, outside the lane loops.
         double sd[kN], cd[kN];
-        if (micro) {
-            AZ_LANES sincos_micro(tho[k], sd[k], cd[k]);
-        } else if (small) {
-            AZ_LANES sincos_tiny(tho[k], sd[k], cd[k]);
-        } else if (!big) {
-            AZ_LANES sincos_quarter(tho[k], sd[k], cd[k]);
-        } else {
-            AZ_LANES sincos_full(tho[k], sd[k], cd[k]);
+        AZ_LANES sincos_micro(tho[k], sd[k], cd[k]);  // the usual case, straight-line; larger angles redo it below
+        if (!micro) {
+            if (small) {
+                AZ_LANES sincos_tiny(tho[k], sd[k], cd[k]);
+            } else if (!big) {
+                AZ_LANES sincos_quarter(tho[k], sd[k], cd[k]);
+            } else {
+                AZ_LANES sincos_full(tho[k], sd[k], cd[k]);
+            }
         }
         AZ_LANES {
             const double sinmm = fma(sm[k], cd[k], cm[k] * sd[k]);
@@ -402,7 +438,6 @@ AZ_HD int resonance_node(double t) {
 template <int kN>
 AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&xli)[kN], const double (&xni)[kN],
                        const double (&atime)[kN], const GravConsts &g, CellOut (&o)[kN], int (&st)[kN]) {
-    constexpr double zns = 1.19459e-5, znl = 1.5835218e-4, zes = 0.01675, zel = 0.05490;
     double tempa[kN], tempe[kN], templ[kN], mm[kN], argpm[kN], nodem[kN], em[kN], inclm[kN], am[kN];
     AZ_LANES {
         st[k] = 0;
@@ -429,7 +464,7 @@ AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&x
             const double xl = fma(xndt[k], hft2, fma(xldot[k], ft, xli[k]));
             // theta = (gsto + t rptim) mod 2pi in the reference; the mean anomaly only ever enters a sine/cosine, whose
             // range reduction absorbs the multiple of 2pi
-            const double theta = fma(t[k], kRptim, e.gsto);
+            const double theta = fma(t[k], AZK(rptim), e.gsto);
             mm[k] = (e.irez == 2) ? xl - 2.0 * nodem[k] + 2.0 * theta : xl - nodem[k] - argpm[k] + theta;
             const double nm = e.no + (nmr - e.no);
             if (nm <= 0.0) st[k] = 1;
@@ -440,11 +475,13 @@ AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&x
                 const double cr = cbrt(g.xke / (nm > 0.0 ? nm : e.no));
                 am[k] = cr * cr * tempa[k] * tempa[k];
             } else {
-                double p = fma(x, 2618.0 / 6561.0, -308.0 / 729.0);  // binomial coefficients of (1 + x)^(-2/3)
-                p = fma(p, x, 110.0 / 243.0);
-                p = fma(p, x, -40.0 / 81.0);
-                p = fma(p, x, 5.0 / 9.0);
-                p = fma(p, x, -2.0 / 3.0);
+                // binomial coefficients of (1 + x)^(-2/3); those of x^3 .. x^6 rounded to 21 significant bits (immediate
+                // operands): on |x| <= 3e-3 that moves the factor by < 7e-15
+                double p = fma(x, 0x1.9899ep-2 /* 2618/6561 */, -0x1.b0a2fp-2 /* -308/729 */);
+                p = fma(p, x, 0x1.cf8ap-2 /* 110/243 */);
+                p = fma(p, x, -0x1.f9addp-2 /* -40/81 */);
+                p = fma(p, x, AZK(bin2));
+                p = fma(p, x, AZK(bin1));
                 am[k] *= fma(p, x, 1.0);
             }
         }
@@ -452,8 +489,8 @@ AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&x
 
     AZ_LANES {
         em[k] -= tempe[k];
-        if (st[k] == 0 && (em[k] >= 1.0 || em[k] < -0.001)) st[k] = 2;
-        em[k] = fmax(em[k], 1.0e-6);
+        if (st[k] == 0 && (ge_one(em[k]) || em[k] < -0.001)) st[k] = 2;
+        em[k] = floor_at(em[k], kHiEmFloor, AZK(emFloor));
         if (st[k] == 0 && am[k] < 0.95) st[k] = 1;
         mm[k] = fma(e.no, templ[k], mm[k]);
     }
@@ -462,11 +499,11 @@ AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&x
     double pe[kN], pinc[kN], pl[kN], pgh[kN], ph[kN];
     {
         double sz[kN], cz[kN];
-        AZ_LANES sincos_full(fma(zns, t[k], e.zmos), sz[k], cz[k]);
+        AZ_LANES sincos_full(fma(AZK(zns), t[k], e.zmos), sz[k], cz[k]);
         AZ_LANES {
             // zf = zm + 2 ze sin(zm): the second sine/cosine is a rotation of the first by an angle below 2 ze
             double sd, cd, sinzf, coszf;
-            sincos_tiny(2.0 * zes * sz[k], sd, cd);  // |.| <= 0.0335
+            sincos_tiny(AZK(zes2) * sz[k], sd, cd);  // |.| <= 0.0335
             rotate(sz[k], cz[k], sd, cd, sinzf, coszf);
             const double f2 = fma(0.5 * sinzf, sinzf, -0.25);
             const double f3 = -0.5 * sinzf * coszf;
@@ -476,10 +513,10 @@ AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&x
             pgh[k] = fma(e.sgh2, f2, fma(e.sgh3, f3, e.sgh4 * sinzf));
             ph[k] = fma(e.sh2, f2, e.sh3 * f3);
         }
-        AZ_LANES sincos_full(fma(znl, t[k], e.zmol), sz[k], cz[k]);
+        AZ_LANES sincos_full(fma(AZK(znl), t[k], e.zmol), sz[k], cz[k]);
         AZ_LANES {
             double sd, cd, sinzf, coszf;
-            sincos_quarter(2.0 * zel * sz[k], sd, cd);  // |.| <= 0.1098
+            sincos_quarter(AZK(zel2) * sz[k], sd, cd);  // |.| <= 0.1098
             rotate(sz[k], cz[k], sd, cd, sinzf, coszf);
             const double f2 = fma(0.5 * sinzf, sinzf, -0.25);
             const double f3 = -0.5 * sinzf * coszf;
@@ -558,9 +595,11 @@ AZ_HD void sdp4_cell_n(const Sdp4Sat &e, const double (&t)[kN], const double (&x
             nodem[k] += kPi;
             argpm[k] -= kPi;
         }
-        em[k] = fmax(em[k], 1.0e-6);
-        if (st[k] == 0 && em[k] >= 1.0) st[k] = 2;
-        if (em[k] >= 1.0) em[k] = 0.5;  // failing lane: keep the shared Kepler loop well conditioned
+        em[k] = floor_at(em[k], kHiEmFloor, AZK(emFloor));
+        if (ge_one(em[k])) {  // failing lane: flag it, and keep the shared Kepler loop well conditioned
+            if (st[k] == 0) st[k] = 2;
+            em[k] = 0.5;
+        }
         if (!(am[k] >= 0.95)) am[k] = 1.0;
         // inclination-dependent terms re-derived per cell (src/Sdp4Batch.zig:326-339)
         const double cosip2 = cosip[k] * cosip[k];

@@ -539,7 +539,7 @@ constexpr int kSdp4Threads = 128;
 constexpr int kSdp4Stripe = 512;
 
 #ifndef AZ_K2_LANES
-#define AZ_K2_LANES 2
+#define AZ_K2_LANES 1
 #endif
 constexpr int kSdp4Lanes = AZ_K2_LANES;  // epochs per thread, 32 apart (each warp-run is 32 consecutive epochs, like K1)
 
@@ -607,7 +607,7 @@ __global__ void __launch_bounds__(kSdp4Threads, kMinBlocks) sdp4_grid_kernel(con
 }
 
 #ifndef AZ_DEFAULT_K2_BLOCKS
-#define AZ_DEFAULT_K2_BLOCKS 3
+#define AZ_DEFAULT_K2_BLOCKS 6
 #endif
 static int g_k2Variant = -1;  // tuning only (ASTROZ_SDP4_VARIANT): 0 -> 3, 1 -> 4, 2 -> 5 resident CTAs per SM
 void set_sdp4_variant(int v) { g_k2Variant = v; }

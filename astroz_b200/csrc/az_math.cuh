@@ -69,6 +69,9 @@ AZ_HD bool abs_lt(double x, uint32_t hiLimit) { return abs_hi(x) < hiLimit; }
 AZ_HD double floor_at(double x, uint32_t hiFloor, double floorValue) {
     return ((int)dbl_hi(x) < (int)hiFloor) ? floorValue : x;
 }
+// x >= 1.0, exactly (1.0 has a zero low word): any double >= 1 has a high word >= 0x3ff00000 as a signed integer,
+// any smaller or negative one does not; NaN compares as >= 1 and is flagged by the callers
+AZ_HD bool ge_one(double x) { return (int)dbl_hi(x) >= 0x3ff00000; }
 // clamp to +-limit (limit given by its high word and value), sign preserved
 AZ_HD double clamp_abs(double x, uint32_t hiLimit, double limit) {
     const uint32_t h = dbl_hi(x);
@@ -111,6 +114,9 @@ struct MathTable {
     double twoOverPi, pio2Hi, pio2Mid, pio2Lo;
     double ts3, ts5, ts7, tc4, tc6, tc8;    // truncated Taylor series for |x| <= 0.05
     double quarterLimit, tinyLimit, clamp, emFloor, keplerTol, invTwoPi, twoPi, pi, microLimit, linearLimit;
+    // deep-space constants (src/Sdp4.zig:15-52): solar / lunar mean motions, twice their eccentricities, the earth's
+    // rotation rate per minute, and the two leading binomial coefficients of (1 + x)^(-2/3)
+    double zns, znl, zes2, zel2, rptim, bin1, bin2;
 };
 #define AZ_MATH_TABLE_INIT                                                                                    \
     {                                                                                                         \
@@ -121,7 +127,8 @@ struct MathTable {
             6.36619772367581382433e-01, AZ_PIO2A, AZ_PIO2B,                                                  \
             -1.49738490485916983692e-33, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 24.0, -1.0 / 720.0,    \
             1.0 / 40320.0, 0.78, 0.05, 0.95, 1.0e-6, 2.0e-15, 1.0 / 6.28318530717958647692528676655900577,    \
-            6.28318530717958647692528676655900577, 3.14159265358979323846264338327950288, 2.0e-3, 1.0e-8      \
+            6.28318530717958647692528676655900577, 3.14159265358979323846264338327950288, 2.0e-3, 1.0e-8,     \
+            1.19459e-5, 1.5835218e-4, 2.0 * 0.01675, 2.0 * 0.05490, 4.37526908801129966e-3, -2.0 / 3.0, 5.0 / 9.0 \
     }
 static __constant__ MathTable kMathDev = AZ_MATH_TABLE_INIT;
 static const MathTable kMathHost = AZ_MATH_TABLE_INIT;

@@ -994,10 +994,10 @@ def test_caller_owned_pageable_and_registered_buffers(az, synth):
     Python, bindings/python/src/satrec.zig:917-942).  Pageable destinations are served through the handle's pinned
     ring + host copy pool, page-locked ones by direct DMA: all three routes must give the same bytes, for blocks that
     span several ring pieces, both layouts, and the strided (wider block) form."""
-    tles = synth.near_earth_catalog(900)
+    tles = synth.near_earth_catalog(2100)
     jd, fr = synth.time_grid(1440)
     c = az.Constellation(tles)
-    n, nt = 900, 1440                                   # 31 MB per array: four 8 MB ring pieces
+    n, nt = 2100, 1440                                  # 72.6 MB per array: three 32 MB ring pieces
     for layout in (az.Layout.satelliteMajor, az.Layout.timeMajor):
         ref_p, ref_v = c.propagate(jd, fr, layout=layout)                     # pinned (the wrapper's own allocation)
         shape = ref_p.shape
