@@ -69,6 +69,41 @@ int32_t status_to_code(int st) {  // kernel-level code -> C API code (src/c_api/
 constexpr size_t kPieceBytes = 32u << 20;
 constexpr int kRingSlots = 3;
 
+// Streaming copy for the landed pieces: the destination is written once and not read again by this library, so the
+// stores bypass the cache (no read-for-ownership of the destination lines, no eviction of the caller's working set):
+// a third less memory traffic per byte than a cached copy.  AVX2 hosts; anything else uses memcpy.
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2"))) static void stream_copy_avx2(char *dst, const char *src, size_t n) {
+    const size_t head = (32 - (reinterpret_cast<uintptr_t>(dst) & 31)) & 31;
+    if (head) {
+        const size_t h = std::min(head, n);
+        std::memcpy(dst, src, h);
+        dst += h; src += h; n -= h;
+    }
+    size_t i = 0;
+    for (; i + 128 <= n; i += 128) {
+        const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i));
+        const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 32));
+        const __m256i c = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 64));
+        const __m256i d = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(src + i + 96));
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i), a);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 32), b);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 64), c);
+        _mm256_stream_si256(reinterpret_cast<__m256i *>(dst + i + 96), d);
+    }
+    _mm_sfence();
+    if (i < n) std::memcpy(dst + i, src + i, n - i);
+}
+static void stream_copy(char *dst, const char *src, size_t n) {
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2 && n >= (64u << 10)) stream_copy_avx2(dst, src, n);
+    else std::memcpy(dst, src, n);
+}
+#else
+static void stream_copy(char *dst, const char *src, size_t n) { std::memcpy(dst, src, n); }
+#endif
+
 class CopyPool {  // process-wide, created on first use, never destroyed (workers sleep on the condition variable)
 public:
     static CopyPool &get() {
@@ -103,7 +138,7 @@ public:
 
 private:
     CopyPool() {
-        int n = 8;
+        int n = 12;
         if (const char *v = std::getenv("ASTROZ_COPY_THREADS")) n = std::max(0, std::min(64, std::atoi(v)));
         const unsigned hw = std::thread::hardware_concurrency();
         if (hw && (unsigned)n > hw) n = (int)hw;
@@ -113,14 +148,14 @@ private:
     // bytes [b0, b1) of the logical contiguous source, scattered to rows of the destination
     static void run(char *dst, const char *src, size_t, size_t, size_t rowBytes, size_t hpitch, size_t b0, size_t b1) {
         if (hpitch == rowBytes) {
-            std::memcpy(dst + b0, src + b0, b1 - b0);
+            stream_copy(dst + b0, src + b0, b1 - b0);
             return;
         }
         size_t b = b0;
         while (b < b1) {
             const size_t r = b / rowBytes, o = b % rowBytes;
             const size_t len = std::min(rowBytes - o, b1 - b);
-            std::memcpy(dst + r * hpitch + o, src + b, len);
+            stream_copy(dst + r * hpitch + o, src + b, len);
             b += len;
         }
     }

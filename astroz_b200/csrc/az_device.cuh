@@ -422,7 +422,7 @@ AZ_HD void resonance_step(const Sdp4Sat &e, double &xli, double &xni, double &at
 // number of whole 720-minute steps the reference's loop `while |t - atime| >= 720` takes from atime = 0
 AZ_HD int resonance_node(double t) {
     const double a = fabs(t);
-    int n = (int)floor(a / kStepp);
+    int n = (int)(a * (1.0 / kStepp));  // a first guess (a division costs ~20 instructions); the two lines below settle it
     if ((double)n * kStepp > a) --n;
     if (a - (double)n * kStepp >= kStepp) ++n;
     return n;

@@ -78,7 +78,7 @@ void astroz_cuda_host_free(void *p);
  * one page-locked with astroz_cuda_host_register (cudaHostRegister: costs about as much as touching the pages once,
  * so it pays for blocks that are reused), receives the result by direct DMA.  Plain pageable memory (a numpy array, a
  * Zig slice from the page allocator) is served through a ring of pinned slots inside the handle: the result leaves the
- * GPU in 32 MB pieces at the full PCIe rate and a small pool of host threads (ASTROZ_COPY_THREADS, default 8) copies
+ * GPU in 32 MB pieces at the full PCIe rate and a small pool of host threads (ASTROZ_COPY_THREADS, default 12, streaming stores) copies
  * each landed piece to its place while the next ones are in flight. */
 int32_t astroz_cuda_host_register(void *p, size_t bytes);
 int32_t astroz_cuda_host_unregister(void *p);
