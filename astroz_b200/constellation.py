@@ -262,6 +262,10 @@ class Constellation:
     def synchronize(self) -> None:
         check(lib().astroz_cuda_constellation_synchronize(self._h))
 
+    def set_timing(self, enabled: bool = True) -> None:
+        """Record CUDA events around the kernels of every later call (off by default: ~12 us of stream time per call)."""
+        check(lib().astroz_cuda_constellation_set_timing(self._h, 1 if enabled else 0))
+
     def last_kernel_ms(self):
         ms = (C.c_float * 3)()
         check(lib().astroz_cuda_constellation_last_kernel_ms(self._h, ms))

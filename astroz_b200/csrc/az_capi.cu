@@ -270,6 +270,8 @@ struct Constellation {
     cudaEvent_t ev[6] = {};  // K1 start/end, K2 start/end, whole call start/end
     cudaEvent_t chunkDone[64] = {};
     bool timed = false, spanTimed = false;
+    bool timing = false;  // kernel-time events are recorded only on request (astroz_cuda_constellation_set_timing): six
+                          // timed event records per call cost ~12 us of stream time, 20 % of a 1/8-catalog step
     int variant = -1;  // -1 = shipped default; >= 0 selects a tuning variant (ASTROZ_SGP4_VARIANT)
     int chunks = 8;
     // Multi-device handle (device = -1 at creation): the catalog is cut into contiguous satellite ranges, one
@@ -348,6 +350,7 @@ int32_t open_device(Constellation *c, int device) {
     for (auto &ev : c->chunkDone) AZ_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     if (const char *v = std::getenv("ASTROZ_SGP4_VARIANT")) c->variant = std::atoi(v);
     if (const char *v = std::getenv("ASTROZ_SDP4_VARIANT")) az::set_sdp4_variant(std::atoi(v));
+    if (const char *v = std::getenv("ASTROZ_TIMING")) c->timing = std::atoi(v) != 0;
     if (const char *v = std::getenv("ASTROZ_K1_STRIPE")) az::set_sgp4_stripe((uint32_t)std::max(0, std::atoi(v)));
     if (const char *v = std::getenv("ASTROZ_D2H_CHUNKS")) c->chunks = std::max(1, std::min(64, std::atoi(v)));
     return ASTROZ_OK;
@@ -619,13 +622,14 @@ int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *
         g_lastError = "internal: satellite-major launches cover the whole time axis";
         return ASTROZ_UNKNOWN;
     }
+    timeIt = timeIt && c->timing;
     const bool doK1 = L.tileCount && t.nSgp4, doK2 = L.deepSpace && t.nSdp4;
     // A mixed call runs its two grids side by side: the deep-space grid is small (a few waves of CTAs at lower
     // fp64-pipe utilisation) and goes first, on the auxiliary stream, so the near-earth CTAs fill the SMs as it drains.
     const bool fork = doK1 && doK2;
     cudaStream_t s2 = fork ? c->auxStream : s;
     if (timeIt) {
-        AZ_CUDA(cudaEventRecord(c->ev[4], s));
+        if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[4], s));
         c->spanTimed = true;
     }
     if (fork) {
@@ -658,8 +662,8 @@ int32_t queue_grid(Constellation *c, const Launch &L, uint32_t ntTotal, double *
         AZ_CUDA(az::launch_sgp4_grid(k1, mode, layout, s, c->variant));
         if (timeIt) AZ_CUDA(cudaEventRecord(c->ev[1], s));
         if (!fork && timeIt) {
-            AZ_CUDA(cudaEventRecord(c->ev[2], s));
-            AZ_CUDA(cudaEventRecord(c->ev[3], s));
+            if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], s));
+            if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], s));
         }
     }
     if (fork) {
@@ -946,7 +950,7 @@ int32_t astroz_cuda_constellation_propagate_device(astroz_constellation_t h, con
     L.tileCount = c->cat.sgp4Tiles_count();
     L.nt = n_times;
     rc = queue_grid(c, L, n_times, d_pos, d_vel, d_status, mode, layout, out_num_sats, out_sat_offset, s, true);
-    c->timed = (rc == ASTROZ_OK);
+    c->timed = (rc == ASTROZ_OK) && c->timing;
     return rc;
 }
 
@@ -982,12 +986,12 @@ static int32_t sdp4_into_common(Constellation *c, const double *jd, const double
     a.nSats = nd;
     a.lattice = c->dLattice.p;
     a.latticeNodes = c->latticeNodes;
-    AZ_CUDA(cudaEventRecord(c->ev[0], s));
-    AZ_CUDA(cudaEventRecord(c->ev[1], s));
-    AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], s));
     AZ_CUDA(az::launch_sdp4_grid(a, mode, layout, s));
-    AZ_CUDA(cudaEventRecord(c->ev[3], s));
-    c->timed = true;
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = c->timing;
     c->spanTimed = false;
     return ASTROZ_OK;
 }
@@ -1075,12 +1079,12 @@ int32_t astroz_cuda_constellation_propagate_device_f32(astroz_constellation_t h,
     a.pos = d_pos;
     a.vel = d_vel;
     a.outNumSats = c->cat.n;
-    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[0], s));
     AZ_CUDA(az::launch_sgp4_grid_f32(a, phase64, s));
-    AZ_CUDA(cudaEventRecord(c->ev[1], s));
-    AZ_CUDA(cudaEventRecord(c->ev[2], s));
-    AZ_CUDA(cudaEventRecord(c->ev[3], s));
-    c->timed = true;
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = c->timing;
     c->spanTimed = false;
     return ASTROZ_OK;
 }
@@ -1124,7 +1128,7 @@ int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, con
     L.nt = n_times;
     rc = queue_grid(c, L, n_times, nullptr, nullptr, nullptr, ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR,
                     out_num_sats, out_sat_offset, s, true, &gt);
-    c->timed = (rc == ASTROZ_OK);
+    c->timed = (rc == ASTROZ_OK) && c->timing;
     return rc;
 }
 
@@ -1230,7 +1234,7 @@ static int32_t propagate_host_queue(Constellation *c, const double *jd, const do
     const uint32_t per = (units + nChunks - 1) / nChunks;
     const bool posPageable = is_pageable(pos), velPageable = vel && is_pageable(vel);
     c->plan.clear();
-    AZ_CUDA(cudaEventRecord(c->ev[4], s));  // whole-call span: first kernel of the first chunk ...
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[4], s));  // whole-call span: first kernel of the first chunk ...
     for (uint32_t k = 0; k < nChunks; ++k) {
         const uint32_t u0 = k * per, u1 = std::min(units, u0 + per);
         if (u0 >= u1) break;
@@ -1269,14 +1273,14 @@ static int32_t propagate_host_queue(Constellation *c, const double *jd, const do
             if (rc != ASTROZ_OK) return rc;
         }
     }
-    AZ_CUDA(cudaEventRecord(c->ev[5], s));  // ... to the last kernel of the last chunk
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[5], s));  // ... to the last kernel of the last chunk
     // last_kernel_ms after a host-buffer call: ms[1] = the span above (all chunks, copies overlapping); the per-kernel
     // slots repeat it
-    AZ_CUDA(cudaEventRecord(c->ev[0], s));
-    AZ_CUDA(cudaEventRecord(c->ev[1], s));
-    AZ_CUDA(cudaEventRecord(c->ev[2], s));
-    AZ_CUDA(cudaEventRecord(c->ev[3], s));
-    c->timed = true;
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = c->timing;
     c->spanTimed = true;
     return ASTROZ_OK;
 }
@@ -1358,6 +1362,18 @@ int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h) {
     AZ_CUDA(cudaSetDevice(c->device));
     AZ_CUDA(cudaStreamSynchronize(c->stream));
     AZ_CUDA(cudaStreamSynchronize(c->copyStream));
+    return ASTROZ_OK;
+}
+
+int32_t astroz_cuda_constellation_set_timing(astroz_constellation_t h, int32_t enabled) {
+    if (!h) return ASTROZ_NULL_POINTER;
+    Constellation *c = static_cast<Constellation *>(h);
+    c->timing = enabled != 0;
+    c->timed = false;
+    for (Constellation *sh : c->shards) {
+        sh->timing = c->timing;
+        sh->timed = false;
+    }
     return ASTROZ_OK;
 }
 
@@ -1449,12 +1465,12 @@ static int32_t sgp4_into_common(Constellation *c, const double *times, uint32_t 
         AZ_CUDA(cudaMemcpyAsync(c->dMask.p, mask, ns, cudaMemcpyHostToDevice, s));
         a.mask = c->dMask.p;
     }
-    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[0], s));
     AZ_CUDA(az::launch_sgp4_grid(a, mode, layout, s, c->variant));
-    AZ_CUDA(cudaEventRecord(c->ev[1], s));
-    AZ_CUDA(cudaEventRecord(c->ev[2], s));
-    AZ_CUDA(cudaEventRecord(c->ev[3], s));
-    c->timed = true;
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = c->timing;
     c->spanTimed = false;
     return ASTROZ_OK;
 }
@@ -1606,12 +1622,12 @@ int32_t astroz_cuda_sgp4_screen(astroz_constellation_t h, const double *times, u
     a.minDist = c->dPos.p + (size_t)n_times * 3;
     a.minT = reinterpret_cast<uint32_t *>(a.minDist + ns);
     a.g = c->g;
-    AZ_CUDA(cudaEventRecord(c->ev[0], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[0], s));
     AZ_CUDA(az::launch_sgp4_screen(a, s));
-    AZ_CUDA(cudaEventRecord(c->ev[1], s));
-    AZ_CUDA(cudaEventRecord(c->ev[2], s));
-    AZ_CUDA(cudaEventRecord(c->ev[3], s));
-    c->timed = true;
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[1], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], s));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], s));
+    c->timed = c->timing;
     c->spanTimed = false;
     AZ_CUDA(cudaMemcpyAsync(out_min_dists, a.minDist, (size_t)ns * 8, cudaMemcpyDeviceToHost, s));
     AZ_CUDA(cudaMemcpyAsync(out_min_t, a.minT, (size_t)ns * 4, cudaMemcpyDeviceToHost, s));
@@ -1899,12 +1915,12 @@ int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *
     a.vel = c->dPos.p + 3;
     a.outNumSats = 1;
     a.recStride = 6;
-    AZ_CUDA(cudaEventRecord(c->ev[0], st));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[0], st));
     AZ_CUDA(az::launch_sgp4_grid(a, ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR, st, c->variant));
-    AZ_CUDA(cudaEventRecord(c->ev[1], st));
-    AZ_CUDA(cudaEventRecord(c->ev[2], st));
-    AZ_CUDA(cudaEventRecord(c->ev[3], st));
-    c->timed = true;
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[1], st));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], st));
+    if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], st));
+    c->timed = c->timing;
     c->spanTimed = false;
     AZ_CUDA(cudaMemcpyAsync(results, c->dPos.p, (size_t)count * 48, cudaMemcpyDeviceToHost, st));
     AZ_CUDA(cudaStreamSynchronize(st));

@@ -658,15 +658,20 @@ AZ_HD void ecef_to_geodetic(double &x, double &y, double &z) {
         z = az - b;
         return;
     }
-    const double ip = rsqrt_nr(p2);
+    // Reciprocal square roots carry one Newton step (2^-46) where that is provably enough: the Heron correction in
+    // sqrt_from_rsqrt squares the error; angle_of_unit is insensitive to a common scale of its arguments (the error is
+    // that scale times its 1e-7-sized residual); the first Bowring evaluation only has to land within the second one's
+    // basin (2e-13 rad), and the height-corrected start needs its 0.7 % term to a few digits.
+    const double ip = rsqrt_nr1(p2);
     const double p = sqrt_from_rsqrt(p2, ip);
     const double lon = angle_of_unit(y * ip, x * ip);
-    const double ir = rsqrt_nr(fma(z, z, p2));
+    const double ir = rsqrt_seed(fma(z, z, p2));
     double su = b * z * fma(ep2b, ir, 1.0), cu = a * p;
     double num = 0.0, den = 1.0;
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
-        const double h = rsqrt_nr(fma(su, su, cu * cu));
+        const double q = fma(su, su, cu * cu);
+        const double h = (it == 0) ? rsqrt_nr1(q) : rsqrt_nr(q);
         su *= h;
         cu *= h;
         num = fma(ep2b * su * su, su, z);
@@ -674,12 +679,12 @@ AZ_HD void ecef_to_geodetic(double &x, double &y, double &z) {
         su = (1.0 - f) * num;
         cu = den;
     }
-    const double h = rsqrt_nr(fma(num, num, den * den));
+    const double h = rsqrt_nr1(fma(num, num, den * den));
     const double sl = num * h, cl = den * h;
     const double w2 = fma(-e2 * sl, sl, 1.0);
     x = angle_of_unit(sl, cl);
     y = lon;
-    z = fma(p, cl, z * sl) - a * sqrt_from_rsqrt(w2, rsqrt_nr(w2));
+    z = fma(p, cl, z * sl) - a * sqrt_from_rsqrt(w2, rsqrt_nr1(w2));
 }
 
 }  // namespace az

@@ -422,13 +422,32 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 #define AZ_DEFAULT_K1 4, 384, 2, 3
 #endif
 #define AZ_COMPACT_K1 4, 256, 3, 2
+// epochs per thread of the time-major and geodetic specialisations (2: the compact shape, 3: the default one)
+#ifndef AZ_TM_LANES
+#define AZ_TM_LANES 2
+#endif
+#ifndef AZ_GEO_LANES
+#define AZ_GEO_LANES 2
+#endif
+#if AZ_TM_LANES == 3
+#define AZ_TIME_MAJOR_K1 AZ_DEFAULT_K1
+#else
+#define AZ_TIME_MAJOR_K1 AZ_COMPACT_K1
+#endif
+#if AZ_GEO_LANES == 3
+#define AZ_GEODETIC_K1 AZ_DEFAULT_K1
+#else
+#define AZ_GEODETIC_K1 AZ_COMPACT_K1
+#endif
 
 // The launch shape (epochs per thread) follows the time axis, identically for the local and the fused all-gather store
 // stages, so a cell is computed by the same instruction stream -- and to the same bits -- whichever way it leaves the SM.
 template <int kLayout, int kMode, bool kVel, int kGather>
 static cudaError_t launch_k1_shaped(const GridArgs &a, cudaStream_t stream) {
-    if constexpr (kLayout == 1 || kMode == 2) {
-        return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1, kGather>(a, stream);
+    if constexpr (kMode == 2) {
+        return launch_k1<kLayout, kMode, kVel, AZ_GEODETIC_K1, kGather>(a, stream);
+    } else if constexpr (kLayout == 1) {
+        return launch_k1<kLayout, kMode, kVel, AZ_TIME_MAJOR_K1, kGather>(a, stream);
     } else {
         // a thread's epochs are 32 apart: short or ragged time axes pad up to 32 * lanes, so take the widest shape
         // that does not add padded warp-runs (16 epochs x 10^6 Monte-Carlo draws: one lane, not three)

@@ -189,6 +189,13 @@ AZ_HD double rsqrt_nr(double x) {
     y = fma(half_of(y), r, y);
     return y;
 }
+// 1/sqrt(x) to ~2^-46 (one Newton step): enough wherever a Heron correction (sqrt_from_rsqrt squares the error), a
+// scale-invariant angle extraction, or a later iteration of the caller's own fixed point follows
+AZ_HD double rsqrt_nr1(double x) {
+    double y = rsqrt_seed(x);
+    const double r = fma(-x * y, y, 1.0);
+    return fma(half_of(y), r, y);
+}
 // sqrt(x) from y ~ 1/sqrt(x): one Heron correction
 AZ_HD double sqrt_from_rsqrt(double x, double y) {
     double s = x * y;

@@ -256,6 +256,12 @@ int32_t astroz_cuda_sgp4_screen_all(astroz_constellation_t h, const double *time
 /* block until everything queued on the handle's stream has finished */
 int32_t astroz_cuda_constellation_synchronize(astroz_constellation_t h);
 
+/* Kernel timing is opt-in: enabled != 0 makes every later propagate call on the handle record CUDA events around its
+ * kernels (about a dozen microseconds of stream time per call, which is why it is off by default; the environment
+ * variable ASTROZ_TIMING=1 turns it on for new handles).  astroz_cuda_constellation_last_kernel_ms returns
+ * ASTROZ_NOT_INITIALIZED for a call made with timing off. */
+int32_t astroz_cuda_constellation_set_timing(astroz_constellation_t h, int32_t enabled);
+
 /* device time (ms, CUDA events on the launching stream) of the propagation kernels of the last
  * propagate call on this handle: [0] SGP4 grid kernel, [1] span of all grid launches of the call (the two grids of a
  * mixed catalog run side by side on two streams, so [1] < [0] + [2] there), [2] SDP4 grid kernel.

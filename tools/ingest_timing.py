@@ -30,6 +30,7 @@ res = {"n_draws": n, "draw_ms": t_draw * 1e3}
 for rep in range(3):
     t0 = time.perf_counter()
     dev = az.Constellation.from_device_elements(el)
+    dev.set_timing(True)
     t_dev = time.perf_counter() - t0
     res.setdefault("device_init_ms", []).append(round(t_dev * 1e3, 3))
     if rep < 2:

@@ -12,6 +12,7 @@ from oracle import oracle as orc   # checker only
 tles = synth.monte_carlo_catalog(10000)
 jd, fr = synth.time_grid(1440, jd0=2460437.5)
 c = Constellation(tles)
+c.set_timing(True)
 dev = torch.device("cuda", 0); n, nt = len(tles), len(jd)
 p64 = torch.empty((n, nt, 3), dtype=torch.float64, device=dev); v64 = torch.empty_like(p64)
 for _ in range(3):

@@ -4,7 +4,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from astroz_b200 import Constellation, synth
-tles = synth.near_earth_catalog(); c = Constellation(tles)
+tles = synth.near_earth_catalog(); c = Constellation(tles); c.set_timing(True)
 times = np.arange(1440.0); ref = 2460437.5; off = (ref - c.epochs) * 1440.0
 for _ in range(3): d, ti = c.screen_conjunction(times, 0, 10.0, epoch_offsets=off, reference_jd=ref)
 t0 = time.perf_counter(); K = 20

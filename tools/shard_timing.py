@@ -42,6 +42,7 @@ for stripe in ("0", "384", "192", "96"):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
         kms = []
+        c.set_timing(True)
         for _ in range(5):
             step()
             c.synchronize()

@@ -37,6 +37,7 @@ pub extern fn astroz_cuda_sgp4_screen(h: Handle, times: ?[*]const f64, n_times: 
 pub extern fn astroz_cuda_constellation_coarse_screen_device(h: Handle, d_positions: ?[*]const f64, num_sats: u32, num_times: u32, layout: i32, threshold: f64, d_valid_mask: ?[*]const u8, d_pairs: ?[*]u32, d_t_indices: ?[*]u32, max_results: u32, count: *u64) i32;
 pub extern fn astroz_cuda_sgp4_screen_all(h: Handle, times: ?[*]const f64, n_times: u32, epoch_offsets: ?[*]const f64, threshold: f64, pairs: ?[*]u32, t_indices: ?[*]u32, max_results: u32, count: *u64) i32;
 pub extern fn astroz_cuda_constellation_synchronize(h: Handle) i32;
+pub extern fn astroz_cuda_constellation_set_timing(h: Handle, enabled: i32) i32;
 pub extern fn astroz_cuda_constellation_last_kernel_ms(h: Handle, ms: *[3]f32) i32;
 pub extern fn astroz_cuda_sgp4_init(line1: [*:0]const u8, line2: [*:0]const u8, grav: i32, device: i32, out: *Handle) i32;
 pub extern fn astroz_cuda_sgp4_free(h: Handle) void;
