@@ -244,7 +244,20 @@ class Harness:
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
                 os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
             torch.cuda.set_device(local_rank)
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            # NCCL prints its version banner on stdout when the first communicator is created; rank 0's stdout carries
+            # exactly one JSON line, so stdout points at stderr until the communicator exists
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+                t = torch.zeros(1, device=torch.device("cuda", local_rank))
+                dist.all_reduce(t)
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
             self.dist = dist
         torch.cuda.set_device(local_rank)
         self.dev = torch.device("cuda", local_rank)
@@ -402,7 +415,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         if c is not None:
             c.synchronize()
             k = c.last_kernel_ms()
-            kms.append(k[1] if k[1] > 0 else k[0] + k[2])  # k[1]: span of the call (the two grids of a mixed catalog overlap)
+            # near-earth only: the events bracketing the one kernel; mixed: the span of the call (its two grids overlap)
+            kms.append(k[0] if n_sdp4_local == 0 else (k[1] if k[1] > 0 else k[0] + k[2]))
     kernel_ms = h.max_over_ranks(float(np.mean(kms)) if kms else 0.0)
     if c is not None:
         c.set_timing(False)
