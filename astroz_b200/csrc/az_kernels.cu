@@ -189,7 +189,11 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
         // slower with velocities on; a CTA-wide 192-byte-row transpose with two barriers per run 11 % slower).
         // The L2 merges the neighbouring pairs' halves of each 32-byte sector before it is written back.
         constexpr int kRun = 32 * kLanes;
-        constexpr int kRow = 7;  // 6 doubles per epoch + 1: a 14-word lane stride is bank-conflict free
+        // The patch IS the pair's slice of the output: 48 contiguous bytes per epoch, epochs back to back.  Lanes write
+        // their 24-byte records at a 48-byte pitch (two-way bank conflict on the stores); the read-back is then one
+        // conflict-free LDS.128 per lane at 16 * lane, and lane = 3 e + ch addresses chunk ch of epoch e with no
+        // division: 30 lanes move 10 epochs per pass.
+        constexpr int kRow = 6;
         __shared__ __align__(16) double tposAll[kWarps * kRun * kRow];
         __shared__ __align__(16) double tvelAll[kVel ? kWarps * kRun * kRow : 2];
         double *tpos = tposAll + warp * kRun * kRow;
@@ -202,19 +206,27 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
             const uint32_t satA = sat0 + 2 * pr;
             const int nPair = min(2, (int)nReal - 2 * pr);
             const uint32_t rowA = __ldg(a.orig + satA);
-            const bool paired = nPair == 2 && a.mask == nullptr && evenStride && __ldg(a.orig + satA + 1) == rowA + 1 &&
+            const uint32_t rowB = nPair == 2 ? __ldg(a.orig + satA + 1) : rowA;
+            const bool actA = !a.mask || a.mask[rowA] != 0;  // laneActive, src/Constellation.zig:530-533
+            const bool actB = nPair == 2 && (!a.mask || a.mask[rowB] != 0);
+            if (!actA && !actB) continue;
+            // both records of an epoch leave as three 16-byte chunks when the pair's rows are adjacent in the block
+            // (an all-near-earth catalog, or a mixed one where no deep-space row falls between them) and 16-byte aligned;
+            // otherwise each satellite's 24 bytes per epoch leave as three 8-byte words -- still transposed through the
+            // patch, so a store instruction covers ten rows' contiguous records instead of 32 rows' single words
+            const bool paired = actA && actB && evenStride && rowB == rowA + 1 &&
                                 ((reinterpret_cast<uintptr_t>(a.pos + (size_t)rowA * 3) & 15u) == 0) &&
                                 (!kVel || (reinterpret_cast<uintptr_t>(a.vel + (size_t)rowA * 3) & 15u) == 0);
 #pragma unroll 1
             for (uint32_t tw = t0; tw < t1; tw += kRun) {
 #pragma unroll 1
                 for (int m = 0; m < nPair; ++m) {
+                    if (!(m == 0 ? actA : actB)) continue;
                     const uint32_t sat = satA + m;
                     const double *colBase = tile + 2 * pr + m;
                     auto col = [colBase](int i) { return colBase[i * kTileSats]; };
                     const double toff = __ldg(a.toff + sat);
-                    const uint32_t row = __ldg(a.orig + sat);
-                    if (a.mask && a.mask[row] == 0) continue;  // laneActive, src/Constellation.zig:530-533
+                    const uint32_t row = m == 0 ? rowA : rowB;
                     double ts[kLanes];
 #pragma unroll
                     for (int k = 0; k < kLanes; ++k) ts[k] = __ldg(a.tbase + min(tw + 32u * k + lane, t1 - 1)) + toff;
@@ -226,33 +238,41 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
                         if (tk >= t1) continue;
                         if (a.status) a.status[(size_t)row * a.nTimes + tk] = (o[k].mrt < 1.0) ? 1 : 0;
                         to_output_frame<kMode, kVel>(a, tk, o[k]);
-                        if (paired) {
-                            double *p = tpos + (32 * k + lane) * kRow + m * 3;
-                            p[0] = o[k].rx; p[1] = o[k].ry; p[2] = o[k].rz;
-                            if (kVel) {
-                                double *v = tvel + (32 * k + lane) * kRow + m * 3;
-                                v[0] = o[k].vx; v[1] = o[k].vy; v[2] = o[k].vz;
-                            }
-                        } else {
-                            store_direct<1, kVel>(a, row, tk, o[k]);
-                        }
-                    }
-                }
-                if (paired) {  // warp-uniform
-                    __syncwarp();
-                    const uint32_t count = min((uint32_t)kRun, t1 - tw);  // epochs in this run
-                    for (uint32_t i = lane; i < count * 3; i += 32) {     // three 16-byte chunks per epoch
-                        const uint32_t j = i / 3, ch = i % 3;
-                        const size_t dst = ((size_t)(tw + j) * a.outNumSats + rowA) * 3 + 2 * ch;
-                        const double *sp = tpos + j * kRow + 2 * ch;
-                        __stcs(reinterpret_cast<double2 *>(a.pos + dst), make_double2(sp[0], sp[1]));
+                        double *p = tpos + (32 * k + lane) * kRow + m * 3;
+                        p[0] = o[k].rx; p[1] = o[k].ry; p[2] = o[k].rz;
                         if (kVel) {
-                            const double *sv = tvel + j * kRow + 2 * ch;
-                            __stcs(reinterpret_cast<double2 *>(a.vel + dst), make_double2(sv[0], sv[1]));
+                            double *v = tvel + (32 * k + lane) * kRow + m * 3;
+                            v[0] = o[k].vx; v[1] = o[k].vy; v[2] = o[k].vz;
                         }
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
+                const uint32_t count = min((uint32_t)kRun, t1 - tw);  // epochs in this run
+                const uint32_t e = (uint32_t)lane / 3u, ch = (uint32_t)lane - 3u * e;  // lane = 3 e + ch; lanes 30, 31 idle
+                const size_t step = (size_t)a.outNumSats * 30;                       // ten epochs, in doubles
+                if (paired) {  // warp-uniform
+                    size_t dst = ((size_t)(tw + e) * a.outNumSats + rowA) * 3 + 2 * ch;
+                    const double2 *sp = reinterpret_cast<const double2 *>(tpos) + lane;
+                    const double2 *sv = reinterpret_cast<const double2 *>(tvel) + lane;
+                    if (lane < 30) {
+                        for (uint32_t j = e; j < count; j += 10, dst += step, sp += 30, sv += 30) {
+                            __stcs(reinterpret_cast<double2 *>(a.pos + dst), *sp);
+                            if (kVel) __stcs(reinterpret_cast<double2 *>(a.vel + dst), *sv);
+                        }
+                    }
+                } else if (lane < 30) {
+#pragma unroll 1
+                    for (int m = 0; m < nPair; ++m) {
+                        if (!(m == 0 ? actA : actB)) continue;
+                        size_t dst = ((size_t)(tw + e) * a.outNumSats + (m == 0 ? rowA : rowB)) * 3 + ch;
+                        const double *sp = tpos + e * kRow + m * 3 + ch, *sv = tvel + e * kRow + m * 3 + ch;
+                        for (uint32_t j = e; j < count; j += 10, dst += step, sp += 10 * kRow, sv += 10 * kRow) {
+                            __stcs(a.pos + dst, *sp);
+                            if (kVel) __stcs(a.vel + dst, *sv);
+                        }
+                    }
+                }
+                __syncwarp();
             }
         }
         return;
@@ -424,13 +444,13 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 #define AZ_COMPACT_K1 4, 256, 3, 2
 // epochs per thread of the time-major and geodetic specialisations (2: the compact shape, 3: the default one)
 #ifndef AZ_TM_LANES
-#define AZ_TM_LANES 2
+#define AZ_TM_LANES 3   // TEME time-major only: measured 40.4 -> 42.9 G props/s; the ECEF rotation wants the registers back
 #endif
 #ifndef AZ_GEO_LANES
 #define AZ_GEO_LANES 2
 #endif
 #if AZ_TM_LANES == 3
-#define AZ_TIME_MAJOR_K1 AZ_DEFAULT_K1
+#define AZ_TIME_MAJOR_K1 4, 384, 3, 3   // three resident CTAs (168-register cap): the transposing patch costs registers
 #else
 #define AZ_TIME_MAJOR_K1 AZ_COMPACT_K1
 #endif
@@ -446,8 +466,10 @@ template <int kLayout, int kMode, bool kVel, int kGather>
 static cudaError_t launch_k1_shaped(const GridArgs &a, cudaStream_t stream) {
     if constexpr (kMode == 2) {
         return launch_k1<kLayout, kMode, kVel, AZ_GEODETIC_K1, kGather>(a, stream);
-    } else if constexpr (kLayout == 1) {
+    } else if constexpr (kLayout == 1 && kMode == 0) {
         return launch_k1<kLayout, kMode, kVel, AZ_TIME_MAJOR_K1, kGather>(a, stream);
+    } else if constexpr (kLayout == 1) {
+        return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1, kGather>(a, stream);
     } else {
         // a thread's epochs are 32 apart: short or ragged time axes pad up to 32 * lanes, so take the widest shape
         // that does not add padded warp-runs (16 epochs x 10^6 Monte-Carlo draws: one lane, not three)

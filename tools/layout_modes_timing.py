@@ -4,7 +4,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from astroz_b200 import Constellation, synth
-tles = synth.near_earth_catalog(); jd, fr = synth.time_grid()
+tles = synth.mixed_catalog() if os.environ.get("AZ_CATALOG") == "mixed" else synth.near_earth_catalog()  # AZ_CATALOG=mixed: config 3
+jd, fr = synth.time_grid()
 dev = torch.device("cuda", 0); n, nt = len(tles), len(jd)
 c = Constellation(tles)
 stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
