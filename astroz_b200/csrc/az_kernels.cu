@@ -211,10 +211,12 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
             const bool actB = nPair == 2 && (!a.mask || a.mask[rowB] != 0);
             if (!actA && !actB) continue;
             // both records of an epoch leave as three 16-byte chunks when the pair's rows are adjacent in the block
-            // (an all-near-earth catalog, or a mixed one where no deep-space row falls between them) and 16-byte aligned;
-            // otherwise each satellite's 24 bytes per epoch leave as three 8-byte words -- still transposed through the
-            // patch, so a store instruction covers ten rows' contiguous records instead of 32 rows' single words
-            const bool paired = actA && actB && evenStride && rowB == rowA + 1 &&
+            // (an all-near-earth catalog, or a mixed one where no deep-space row falls between them) and 16-byte aligned,
+            // as six 8-byte words when adjacent but unaligned; a satellite without its partner (masked, or a deep-space
+            // row in between) leaves as three 8-byte words per epoch -- always transposed through the patch, so a store
+            // instruction covers whole contiguous records of 5-10 rows instead of 32 rows' single words
+            const bool adjacent = actA && actB && rowB == rowA + 1;  // the pair's 48 bytes per epoch are contiguous
+            const bool paired = adjacent && evenStride &&
                                 ((reinterpret_cast<uintptr_t>(a.pos + (size_t)rowA * 3) & 15u) == 0) &&
                                 (!kVel || (reinterpret_cast<uintptr_t>(a.vel + (size_t)rowA * 3) & 15u) == 0);
 #pragma unroll 1
@@ -258,6 +260,20 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
                         for (uint32_t j = e; j < count; j += 10, dst += step, sp += 30, sv += 30) {
                             __stcs(reinterpret_cast<double2 *>(a.pos + dst), *sp);
                             if (kVel) __stcs(reinterpret_cast<double2 *>(a.vel + dst), *sv);
+                        }
+                    }
+                } else if (adjacent) {
+                    // contiguous but not 16-byte aligned (odd first row, or an odd row count): the pair's six words per
+                    // epoch as 8-byte stores, lane = 6 e + w -- a store instruction still fills whole 48-byte runs (five
+                    // rows per pass), half the cache-line visits of storing the two satellites separately
+                    const uint32_t e6 = (uint32_t)lane / 6u, w = (uint32_t)lane - 6u * e6;
+                    if (lane < 30) {
+                        size_t dst = ((size_t)(tw + e6) * a.outNumSats + rowA) * 3 + w;
+                        const size_t step5 = (size_t)a.outNumSats * 15;
+                        const double *sp = tpos + lane, *sv = tvel + lane;
+                        for (uint32_t j = e6; j < count; j += 5, dst += step5, sp += 30, sv += 30) {
+                            __stcs(a.pos + dst, *sp);
+                            if (kVel) __stcs(a.vel + dst, *sv);
                         }
                     }
                 } else if (lane < 30) {
