@@ -604,6 +604,7 @@ template <int kLayout, int kMode, bool kVel, int kGather, int kMinBlocks>
 __global__ void __launch_bounds__(kSdp4Threads, kMinBlocks) sdp4_grid_kernel(const GridArgs a) {
     __shared__ Sdp4Sat e;
     __shared__ __align__(16) double stageAll[kGather != 0 ? (kSdp4Threads / 32) * 2 * kStageDoubles : 2];
+    __shared__ __align__(16) double tmPatch[(kLayout == 1 && kGather == 0) ? (kSdp4Threads / 32) * (kVel ? 192 : 96) : 2];
     const uint32_t sat = blockIdx.x;
     {
         const double *src = reinterpret_cast<const double *>(a.sdp4 + sat);
@@ -656,6 +657,28 @@ __global__ void __launch_bounds__(kSdp4Threads, kMinBlocks) sdp4_grid_kernel(con
             }
             if (kGather != 0) {
                 emit_run_sat_major<kVel, kGather>(a, row, twk, min(32u, t1 - twk), lane, valid, o[k], stage);
+            } else if (kLayout == 1) {
+                // time-major: the warp's 32 records of this satellite sit n_sats * 24 bytes apart.  Transposed through
+                // the warp's patch they leave as whole 24-byte records, lane = 3 e + w, ten rows per store instruction,
+                // instead of one word of 32 different rows each
+                double *tp = tmPatch + warp * (kVel ? 192 : 96);
+                if (valid) {
+                    tp[lane * 3 + 0] = o[k].rx; tp[lane * 3 + 1] = o[k].ry; tp[lane * 3 + 2] = o[k].rz;
+                    if (kVel) { tp[96 + lane * 3 + 0] = o[k].vx; tp[96 + lane * 3 + 1] = o[k].vy; tp[96 + lane * 3 + 2] = o[k].vz; }
+                }
+                __syncwarp();
+                const uint32_t count = min(32u, t1 - twk);
+                const uint32_t e = (uint32_t)lane / 3u, w = (uint32_t)lane - 3u * e;
+                if (lane < 30) {
+                    size_t dst = ((size_t)(twk + e) * a.outNumSats + row) * 3 + w;
+                    const size_t step = (size_t)a.outNumSats * 30;
+                    const double *sp = tp + lane;
+                    for (uint32_t j = e; j < count; j += 10, dst += step, sp += 30) {
+                        __stcs(a.pos + dst, *sp);
+                        if (kVel) __stcs(a.vel + dst, sp[96]);
+                    }
+                }
+                __syncwarp();
             } else if (valid) {
                 store_direct<kLayout, kVel>(a, row, t, o[k]);
             }
