@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
         "astroz_cuda_constellation_synchronize": (i32, [vp]),
         "astroz_cuda_constellation_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
         "astroz_cuda_constellation_set_timing": (i32, [vp, i32]),
+        "astroz_cuda_constellation_host_block": (i32, [vp, u32, i32, C.POINTER(vp)]),
         "astroz_cuda_sgp4_propagate_into": (i32, [vp, dp, u32, dp, dp, dp, i32, C.c_double, i32, vp, u32]),
         "astroz_cuda_sgp4_propagate_into_device": (i32, [vp, dp, u32, dp, vp, vp, i32, C.c_double, i32, vp, u32, vp]),
         "astroz_cuda_sdp4_propagate_into": (i32, [vp, dp, dp, u32, dp, dp, i32, i32, u32, u32]),
@@ -130,7 +131,7 @@ EXPORTS = [
     "astroz_cuda_sgp4_propagate", "astroz_cuda_sgp4_propagate_batch", "astroz_cuda_sgp4_array",
     "astroz_cuda_fp64_peak", "astroz_cuda_fp64_pipe_peak", "astroz_cuda_constellation_devices",
     "astroz_cuda_constellation_propagate_replicated", "astroz_cuda_host_register", "astroz_cuda_host_unregister",
-    "astroz_cuda_constellation_set_timing",
+    "astroz_cuda_constellation_set_timing", "astroz_cuda_constellation_host_block",
 ]
 
 

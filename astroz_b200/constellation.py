@@ -131,6 +131,16 @@ class Constellation:
         check(lib().astroz_cuda_constellation_devices(self._h, C.byref(n), ids, rows))
         return list(ids), list(rows)
 
+    def host_block(self, n_times: int, layout: int = Layout.satelliteMajor) -> np.ndarray:
+        """A page-locked (n, n_times, 3) / (n_times, n, 3) result block placed for this handle: on a multi-device handle
+        each GPU's satellite range sits on that GPU's NUMA node.  Released when the array is collected."""
+        p = C.c_void_p()
+        check(lib().astroz_cuda_constellation_host_block(self._h, int(n_times), int(layout), C.byref(p)))
+        shape = self._shape(int(n_times), layout)
+        nbytes = int(np.prod(shape)) * 8
+        owner = _HostBlock(p.value, nbytes)
+        return np.asarray(owner).view(np.float64).reshape(shape)
+
     def propagate_replicated(self, jd, fr, velocities: bool = True):
         """The north star's all-gather behind one (multi-device) handle: TEME, satellite-major; the whole
         (n, n_times, 3) block(s) end up in the HBM of every device of the handle, stored there from inside the
@@ -395,6 +405,22 @@ class Constellation:
         if cnt.value > max_results:
             raise AstrozCudaError(-20, f"{cnt.value} hits exceed max_results={max_results}")
         return _sorted_hits(pairs[:cnt.value], tidx[:cnt.value])
+
+
+class _HostBlock:
+    """Owner of a block from astroz_cuda_constellation_host_block (array interface; freed with the last view)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr = ptr
+        self.__array_interface__ = {"shape": (max(nbytes, 1),), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            try:
+                lib().astroz_cuda_host_free(C.c_void_p(self.ptr))
+            except Exception:
+                pass
+            self.ptr = None
 
 
 def _sorted_hits(pairs: np.ndarray, tidx: np.ndarray):

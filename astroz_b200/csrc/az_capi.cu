@@ -9,7 +9,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+
 #include <atomic>
+#include <map>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -26,6 +31,8 @@
 namespace {
 
 thread_local std::string g_lastError;
+std::mutex g_blockMutex;
+std::map<void *, size_t> g_blocks;  // blocks made by astroz_cuda_constellation_host_block: host_free unregisters + unmaps
 
 int32_t cuda_fail(cudaError_t e, const char *what) {
     g_lastError = std::string(what) + ": " + cudaGetErrorString(e);
@@ -770,7 +777,22 @@ void *astroz_cuda_host_alloc(size_t bytes) {
     return p;
 }
 void astroz_cuda_host_free(void *p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    size_t mapped = 0;
+    {
+        std::lock_guard<std::mutex> g(g_blockMutex);
+        auto it = g_blocks.find(p);
+        if (it != g_blocks.end()) {
+            mapped = it->second;
+            g_blocks.erase(it);
+        }
+    }
+    if (mapped) {  // a block from astroz_cuda_constellation_host_block
+        cudaHostUnregister(p);
+        munmap(p, mapped);
+        return;
+    }
+    cudaFreeHost(p);
 }
 
 int32_t astroz_cuda_constellation_create(const char *const *line1, const char *const *line2, uint32_t n, int32_t grav,
@@ -1231,7 +1253,11 @@ static int32_t propagate_host_queue(Constellation *c, const double *jd, const do
     uint32_t units = bySat ? tiles : (byTime ? n_times : 1);
     uint32_t nChunks = (bySat || byTime) ? std::min<uint32_t>((uint32_t)c->chunks, units) : 1;
     if (total * 8 < (8u << 20)) nChunks = 1;
-    const uint32_t per = (units + nChunks - 1) / nChunks;
+    uint32_t per = (units + nChunks - 1) / nChunks;
+    // a thread's epochs are 32 apart and the kernels start their runs at multiples of 64 / 96 epochs from the start of the
+    // launch: time chunks that start on multiples of 192 keep every thread's set of epochs -- and with it the series each
+    // cell takes, i.e. every result bit -- the same however the call is chunked (one device or many, any chunk count)
+    if (byTime && nChunks > 1) per = (per + 191) / 192 * 192;
     const bool posPageable = is_pageable(pos), velPageable = vel && is_pageable(vel);
     c->plan.clear();
     if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[4], s));  // whole-call span: first kernel of the first chunk ...
@@ -1934,6 +1960,74 @@ int32_t astroz_cuda_sgp4_propagate(astroz_sgp4_t h, double tsince, double pos[3]
     std::memcpy(pos, r, 24);
     std::memcpy(vel, r + 3, 24);
     return rc;
+}
+
+// ---- result blocks placed next to the GPUs that fill them ---------------------------------------------------------
+// A multi-device handle writes one host block from several GPUs at once.  A plain pinned allocation sits on the NUMA
+// node of the thread that made it, so half the GPUs of a two-socket box write across the socket interconnect and all of
+// them into one node's memory controllers (measured: 93 GB/s for 8 GPUs against 315 GB/s when every GPU writes node-local
+// memory).  astroz_cuda_constellation_host_block maps the block anonymously, binds each device's slice of a
+// satellite-major block to the NUMA node of that device (mbind), touches it, and page-locks the whole range.
+static int device_numa_node(int device) {
+    char bus[32] = {};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return -1;
+    }
+    for (char *p = bus; *p; ++p) *p = (char)std::tolower(*p);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/numa_node";
+    FILE *f = std::fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (std::fscanf(f, "%d", &node) != 1) node = -1;
+    std::fclose(f);
+    return node;
+}
+
+static void bind_to_node(char *begin, char *end, int node) {
+#ifdef SYS_mbind
+    if (node < 0 || node >= 64) return;
+    const long page = sysconf(_SC_PAGESIZE);
+    char *b = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(begin) + page - 1) / page * page);
+    char *e = reinterpret_cast<char *>(reinterpret_cast<uintptr_t>(end) / page * page);
+    if (e <= b) return;
+    unsigned long mask = 1ul << node;
+    (void)syscall(SYS_mbind, b, (unsigned long)(e - b), 2 /* MPOL_BIND */, &mask, 64ul, 0u);  // best effort
+#else
+    (void)begin; (void)end; (void)node;
+#endif
+}
+
+int32_t astroz_cuda_constellation_host_block(astroz_constellation_t h, uint32_t n_times, int32_t layout, double **out) {
+    if (!h || !out) return ASTROZ_NULL_POINTER;
+    *out = nullptr;
+    Constellation *c = static_cast<Constellation *>(h);
+    const size_t bytes = std::max<size_t>((size_t)c->cat.n * n_times * 24, 4096);
+    void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) return ASTROZ_ALLOC_FAILED;
+    char *base = static_cast<char *>(p);
+    if (c->multi() && layout == ASTROZ_LAYOUT_SATELLITE_MAJOR) {
+        for (size_t k = 0; k < c->shards.size(); ++k)
+            bind_to_node(base + (size_t)c->shardRow0[k] * n_times * 24, base + (size_t)c->shardRow0[k + 1] * n_times * 24,
+                         device_numa_node(c->shards[k]->device));
+    } else if (!c->multi()) {
+        bind_to_node(base, base + bytes, device_numa_node(c->device));
+    }   // time-major over several devices: rows interleave, the default (first-touch) placement stays
+    {   // touch every page so the placement happens now, on the bound node, not at the first DMA
+        const long page = sysconf(_SC_PAGESIZE);
+        for (size_t o = 0; o < bytes; o += (size_t)page) base[o] = 0;
+    }
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        munmap(p, bytes);
+        return cuda_fail(e, "cudaHostRegister");
+    }
+    {
+        std::lock_guard<std::mutex> g(g_blockMutex);
+        g_blocks[p] = bytes;
+    }
+    *out = static_cast<double *>(p);
+    return ASTROZ_OK;
 }
 
 // ---- caller-owned buffers: explicit page-locking ------------------------------------------------------------

@@ -454,8 +454,17 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 // on-device sweeps in profiles/: the plain satellite-major TEME/ECEF grid likes three epochs per thread (more
 // independent fp64 chains per warp, 158 registers, 2 CTAs/SM: -2.2 %); the time-major transpose and the geodetic
 // epilogue need the registers themselves and are faster with two.
+#ifndef AZ_K1_STRIPE
+#define AZ_K1_STRIPE 384
+#endif
+#ifndef AZ_K1_BLOCKS
+#define AZ_K1_BLOCKS 2
+#endif
+#ifndef AZ_K1_LANES
+#define AZ_K1_LANES 3
+#endif
 #ifndef AZ_DEFAULT_K1
-#define AZ_DEFAULT_K1 4, 384, 2, 3
+#define AZ_DEFAULT_K1 4, AZ_K1_STRIPE, AZ_K1_BLOCKS, AZ_K1_LANES
 #endif
 #define AZ_COMPACT_K1 4, 256, 3, 2
 // epochs per thread of the time-major and geodetic specialisations (2: the compact shape, 3: the default one)

@@ -244,20 +244,7 @@ class Harness:
             if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
                 os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's banner off stdout: rank 0 prints ONE JSON line
             torch.cuda.set_device(local_rank)
-            # NCCL prints its version banner on stdout when the first communicator is created; rank 0's stdout carries
-            # exactly one JSON line, so stdout points at stderr until the communicator exists
-            sys.stdout.flush()
-            saved = os.dup(1)
-            os.dup2(2, 1)
-            try:
-                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-                t = torch.zeros(1, device=torch.device("cuda", local_rank))
-                dist.all_reduce(t)
-                torch.cuda.synchronize()
-            finally:
-                sys.stdout.flush()
-                os.dup2(saved, 1)
-                os.close(saved)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
             self.dist = dist
         torch.cuda.set_device(local_rank)
         self.dev = torch.device("cuda", local_rank)
@@ -306,14 +293,20 @@ class Harness:
 
 
 def e2e_leg(h: Harness, c, jd, fr, rows: int, layout: int, mode: int, velocities: bool, pinned: bool, reps: int,
-            total_cells: int, what: str) -> dict:
+            total_cells: int, what: str, alloc=None) -> dict:
     """One host-to-host call shape through Constellation.propagate: host time axis in, host result block out, the
     result read on the host every step.  `rows` = satellites of this rank's shard."""
     import astroz_b200
 
     nt = len(jd)
     shape = (rows, nt, 3) if layout == 0 else (nt, rows, 3)
-    alloc = astroz_b200.pinned_empty if pinned else (lambda s: np.zeros(s))   # zeros: pages touched before the clock
+    buffers = "pinned (astroz_cuda_host_alloc)" if pinned else "caller-owned pageable (numpy)"
+    if alloc is not None:
+        buffers = "pinned, each GPU's rows on its NUMA node (astroz_cuda_constellation_host_block)"
+    elif pinned:
+        alloc = astroz_b200.pinned_empty
+    else:
+        alloc = lambda s: np.zeros(s)   # noqa: E731  zeros: pages touched before the clock
     hp = alloc(shape) if rows else None
     hv = alloc(shape) if (rows and velocities) else None
 
@@ -332,7 +325,7 @@ def e2e_leg(h: Harness, c, jd, fr, rows: int, layout: int, mode: int, velocities
     sec = h.max_over_ranks(time.perf_counter() - t0) / reps
     per_cell = 48 if velocities else 24
     return {"value": total_cells / sec, "unit": "props/s", "ms_per_step": sec * 1e3, "what": what,
-            "buffers": "pinned (astroz_cuda_host_alloc)" if pinned else "caller-owned pageable (numpy)",
+            "buffers": buffers,
             "h2d_bytes_per_step": 2 * nt * 8, "d2h_bytes_per_step": total_cells * per_cell,
             "d2h_GBs": total_cells * per_cell / sec / 1e9, "checksum": checksum}
 
@@ -359,6 +352,12 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: astroz_b200 has no CPU propagation path")
+    # Rank 0's stdout carries exactly ONE JSON line.  NCCL (version banner at communicator creation) and other native
+    # libraries write to file descriptor 1 directly, so for the whole run fd 1 points at stderr and the line is written to
+    # the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     h = Harness(rank, local_rank, world)
     dev, stream, dist = h.dev, h.stream, h.dist
     affinity0 = os.sched_getaffinity(0) if world > 1 else None
@@ -449,9 +448,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                 multi = Constellation(tles, device=-1)
                 ids, first_rows = multi.devices
                 leg = e2e_leg(Harness.solo(h), multi, jd, fr, n, 0, 0, True, True, e2e_steps, cells,
-                              f"ONE Constellation handle over {len(ids)} GPUs (device = -1), one process, one propagate call")
+                              f"ONE Constellation handle over {len(ids)} GPUs (device = -1), one process, one propagate call",
+                              alloc=lambda shape: multi.host_block(shape[1], 0))
                 leg["devices"] = ids
                 legs["single_handle_all_gpus"] = leg
+                legs["single_handle_all_gpus_plain_pinned"] = e2e_leg(
+                    Harness.solo(h), multi, jd, fr, n, 0, 0, True, True, e2e_steps, cells,
+                    "same, result blocks from astroz_cuda_host_alloc (all on one NUMA node)")
                 del multi
             except Exception as exc:
                 legs["single_handle_all_gpus"] = {"unavailable": repr(exc)[:300]}
@@ -561,7 +564,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         out["config3"] = config3
     if config4 is not None:
         out["config4"] = config4
-    print(json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 

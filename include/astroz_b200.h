@@ -169,6 +169,12 @@ int32_t astroz_cuda_constellation_propagate_gather(astroz_constellation_t h, con
                                                    uint32_t n_peers, void *mc_pos, void *mc_vel,
                                                    uint32_t out_num_sats, uint32_t out_sat_offset, void *stream);
 
+/* A page-locked result block of n * n_times * 3 doubles placed for the handle that will fill it: on a multi-device
+ * handle each device's satellite range of a satellite-major block is bound to the NUMA node that device hangs off
+ * (mbind), so every GPU writes node-local host memory over its own PCIe link -- a plain pinned allocation lives on one
+ * node and was measured at 93 GB/s for 8 GPUs against 315 GB/s node-local.  Free with astroz_cuda_host_free. */
+int32_t astroz_cuda_constellation_host_block(astroz_constellation_t h, uint32_t n_times, int32_t layout, double **out);
+
 /* Devices behind a handle: *n_devices (1 for a single-device handle); device_ids[n_devices] (nullable) their CUDA
  * ordinals; first_rows[n_devices + 1] (nullable) the first catalog row of each device's satellite range, then n. */
 int32_t astroz_cuda_constellation_devices(astroz_constellation_t h, int32_t *n_devices, int32_t *device_ids,
