@@ -58,6 +58,9 @@ def test_one_handle_over_all_gpus_matches_one_gpu():
         pm, vm = multi.propagate(jd, fr, layout=layout)
         assert np.array_equal(ps, pm) and np.array_equal(vs, vm)
     ps, vs = single.propagate(jd, fr, layout=0)
+    blk_p, blk_v = multi.host_block(len(jd), 0), multi.host_block(len(jd), 0)   # each GPU's rows on its own NUMA node
+    multi.propagate(jd, fr, blk_p, blk_v, layout=0)
+    assert np.array_equal(blk_p, ps) and np.array_equal(blk_v, vs)
     ids, ppos, pvel = multi.propagate_replicated(jd, fr)
     from cuda import cudart
 

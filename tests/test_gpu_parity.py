@@ -1011,6 +1011,13 @@ def test_caller_owned_pageable_and_registered_buffers(az, synth):
         finally:
             az.host_unregister(rg_p)
         assert np.array_equal(rg_p, ref_p)
+    # a result block placed by the library for the handle (NUMA-bound, page-locked; freed with the array)
+    for layout in (az.Layout.satelliteMajor, az.Layout.timeMajor):
+        blk = c.host_block(nt, layout)
+        assert blk.shape == ((n, nt, 3) if layout == 0 else (nt, n, 3)) and blk.dtype == np.float64
+        c.propagate(jd, fr, blk, None, layout=layout, velocities=False)
+        assert np.array_equal(blk, c.propagate(jd, fr, layout=layout, velocities=False)[0])
+        del blk
     # stateless path into a wider pageable block: rows beyond the constellation and the pitch gaps stay untouched
     times = np.arange(0.0, 1440.0, 1.0)
     off = (2460437.5 - c.epochs) * 1440.0
