@@ -510,6 +510,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     if os.path.exists(tfile) and world == 1:
         try:
             traffic = json.load(open(tfile)).get(args.workload)
+            if isinstance(traffic, dict):
+                traffic = traffic.get("total")
         except Exception:
             traffic = None
     roofline = {
