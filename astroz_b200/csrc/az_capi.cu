@@ -1910,33 +1910,78 @@ int32_t astroz_cuda_sgp4_array(astroz_sgp4_t h, const double *jd, const double *
     AZ_CUDA(cudaSetDevice(c->device));
     cudaStream_t st = c->stream;
     c->cacheValid = false;
-    AZ_CUDA(c->dTime.reserve((size_t)count * 2));
-    AZ_CUDA(c->dPos.reserve((size_t)count * 6));
-    AZ_CUDA(cudaMemcpyAsync(c->dTime.p, jd, (size_t)count * 8, cudaMemcpyHostToDevice, st));
-    AZ_CUDA(cudaMemcpyAsync(c->dTime.p + count, fr, (size_t)count * 8, cudaMemcpyHostToDevice, st));
-    az::GridArgs a;
-    a.g = c->g;
-    a.sgp4Tiles = c->dTiles.p;
-    a.toff = c->dToff.p;
-    a.orig = c->dIdentity.p;
-    a.nSats = 1;
-    a.jdArr = c->dTime.p;
-    a.frArr = c->dTime.p + count;
-    a.tbase = c->dTime.p;
-    a.epochJd = epoch_jd;
-    a.nTimes = count;
-    a.pos = c->dPos.p;
-    a.vel = c->dPos.p + 3;
-    a.outNumSats = 1;
-    a.recStride = 6;
+    // A long axis ("1 year at one second" = 31.5 M epochs: 0.5 GB of jd/fr in, 1.5 GB of records out) is cut into
+    // chunks on a two-slot pipeline: while chunk k is propagated, chunk k+1's epochs are staged and uploaded and chunk
+    // k-1's records travel back, so the call runs at the PCIe rate of its 48 B/epoch result instead of the sum of three
+    // serial phases.  jd / fr usually are pageable (numpy): the copy pool stages them into pinned slots.
+    constexpr uint32_t kChunk = 1u << 21;   // epochs per chunk: 32 MB of epochs, 96 MB of records
+    const uint32_t nChunks = (count + kChunk - 1) / kChunk;
+    const uint32_t chunk = ((count + nChunks - 1) / nChunks + 31) / 32 * 32;   // balanced: no short last chunk
+    const int slots = nChunks > 1 ? 2 : 1;
+    AZ_CUDA(c->dTime.reserve((size_t)chunk * 2 * slots));
+    AZ_CUDA(c->dPos.reserve((size_t)chunk * 6 * slots));
+    const bool inPageable = is_pageable(jd) || is_pageable(fr);
+    const bool outPageable = is_pageable(results);
+    if ((inPageable || outPageable) && !c->ring) {
+        AZ_CUDA(cudaMallocHost(&c->ring, kPieceBytes * kRingSlots));
+        for (auto &e : c->ringEv) AZ_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    // pinned staging inside the ring allocation (96 MB): two 16 MB input slots [jd | fr]; outputs of a pageable caller
+    // are not staged here (a 96 MB chunk does not fit) -- they go through cudaMemcpyAsync's own staging
+    CopyPool &pool = CopyPool::get();
+    cudaEvent_t kdone[2] = {c->chunkDone[0], c->chunkDone[1]}, ddone[2] = {c->chunkDone[2], c->chunkDone[3]};
+    const uint32_t inChunk = inPageable ? std::min<uint32_t>(chunk, (uint32_t)(kPieceBytes / 16)) : chunk;  // staging granule
     if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[0], st));
-    AZ_CUDA(az::launch_sgp4_grid(a, ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR, st, c->variant));
+    uint32_t granule = 0;
+    for (uint32_t k = 0; k < nChunks; ++k) {
+        const int slot = (int)(k & 1u) % slots;
+        const uint32_t t0 = k * chunk, n = std::min(chunk, count - t0);
+        double *dJd = c->dTime.p + (size_t)slot * chunk * 2, *dFr = dJd + chunk;
+        double *dOut = c->dPos.p + (size_t)slot * chunk * 6;
+        if (k >= (uint32_t)slots) AZ_CUDA(cudaEventSynchronize(ddone[slot]));  // chunk k-2 has left this slot
+        if (inPageable) {   // stage through pinned memory in granules of the ring slot size, copy pool does the memcpy
+            for (uint32_t g0 = 0; g0 < n; g0 += inChunk, ++granule) {
+                const uint32_t gn = std::min(inChunk, n - g0);
+                const int ri = (int)(granule % kRingSlots);
+                char *stage = c->ring + (size_t)ri * kPieceBytes;
+                if (granule >= (uint32_t)kRingSlots) AZ_CUDA(cudaEventSynchronize(c->ringEv[ri]));  // its last upload is done
+                pool.copy(stage, reinterpret_cast<const char *>(jd + t0 + g0), 1, (size_t)gn * 8, (size_t)gn * 8);
+                pool.copy(stage + (size_t)gn * 8, reinterpret_cast<const char *>(fr + t0 + g0), 1, (size_t)gn * 8, (size_t)gn * 8);
+                AZ_CUDA(cudaMemcpyAsync(dJd + g0, stage, (size_t)gn * 8, cudaMemcpyHostToDevice, st));
+                AZ_CUDA(cudaMemcpyAsync(dFr + g0, stage + (size_t)gn * 8, (size_t)gn * 8, cudaMemcpyHostToDevice, st));
+                AZ_CUDA(cudaEventRecord(c->ringEv[ri], st));
+            }
+        } else {
+            AZ_CUDA(cudaMemcpyAsync(dJd, jd + t0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+            AZ_CUDA(cudaMemcpyAsync(dFr, fr + t0, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+        }
+        az::GridArgs a;
+        a.g = c->g;
+        a.sgp4Tiles = c->dTiles.p;
+        a.toff = c->dToff.p;
+        a.orig = c->dIdentity.p;
+        a.nSats = 1;
+        a.jdArr = dJd;
+        a.frArr = dFr;
+        a.tbase = dJd;
+        a.epochJd = epoch_jd;
+        a.nTimes = n;
+        a.pos = dOut;
+        a.vel = dOut + 3;
+        a.outNumSats = 1;
+        a.recStride = 6;
+        AZ_CUDA(az::launch_sgp4_grid(a, ASTROZ_MODE_TEME, ASTROZ_LAYOUT_SATELLITE_MAJOR, st, c->variant));
+        AZ_CUDA(cudaEventRecord(kdone[slot], st));
+        AZ_CUDA(cudaStreamWaitEvent(c->copyStream, kdone[slot], 0));
+        AZ_CUDA(cudaMemcpyAsync(results + (size_t)t0 * 6, dOut, (size_t)n * 48, cudaMemcpyDeviceToHost, c->copyStream));
+        AZ_CUDA(cudaEventRecord(ddone[slot], c->copyStream));
+    }
     if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[1], st));
     if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[2], st));
     if (c->timing) AZ_CUDA(cudaEventRecord(c->ev[3], st));
     c->timed = c->timing;
     c->spanTimed = false;
-    AZ_CUDA(cudaMemcpyAsync(results, c->dPos.p, (size_t)count * 48, cudaMemcpyDeviceToHost, st));
+    AZ_CUDA(cudaStreamSynchronize(c->copyStream));
     AZ_CUDA(cudaStreamSynchronize(st));
     return ASTROZ_OK;
 }

@@ -525,6 +525,31 @@ def test_single_satellite_long_time_axis(az, oracle):
     assert _maxerr(p2[0], r[:3000]) < 1e-6 and np.array_equal(p2[0], p2[1])
 
 
+def test_single_satellite_chunked_pipeline(az, oracle):
+    """An axis long enough for the chunked upload / propagate / download pipeline of astroz_cuda_sgp4_array (three
+    chunks of 1.5 M epochs): chunk seams, the pageable-input staging and the pinned result must all line up."""
+    from astroz_b200.api import Satrec, WGS72
+
+    sat = Satrec.twoline2rv(*G.ISS, WGS72)
+    n = 4_500_007
+    jd = np.full(n, sat.jdsatepoch)
+    fr = sat.jdsatepochF + np.arange(n) * (1.0 / 86400.0)
+    e, r, v = sat.sgp4_array(jd, fr)
+    assert r.shape == (n, 3) and np.isfinite(r).all() and np.isfinite(v).all()
+    ts = ((jd + fr) - (sat.jdsatepoch + sat.jdsatepochF)) * 1440.0
+    ref = oracle.Sgp4(*G.ISS, grav=oracle.WGS72)
+    seams = [1_500_032, 3_000_064]
+    idx = np.r_[0:8, n - 8:n, np.arange(0, n, 150_001)]
+    for sm in seams:
+        idx = np.r_[idx, sm - 4:sm + 4]
+    ro = np.array([ref.propagate(ts[i]) for i in idx])
+    assert _maxerr(r[idx], ro[:, 0]) < POS_TOL and _maxerr(v[idx], ro[:, 1]) < VEL_TOL
+    # a window across the first seam, propagated on its own (one chunk), agrees to rounding
+    a, b = seams[0] - 10_000, seams[0] + 10_000
+    _, r2, v2 = sat.sgp4_array(jd[a:b], fr[a:b])
+    assert _maxerr(r2, r[a:b]) < 1e-9 and _maxerr(v2, v[a:b]) < 1e-12
+
+
 def test_config5_monte_carlo_draws_and_fp32_study(az, oracle, synth):
     """BASELINE config 5: perturbed draws of one object.  fp64 kernel vs oracle at the usual tolerance; the fp32
     study kernels must stay within the (much looser) envelope single precision allows."""

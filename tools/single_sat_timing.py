@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from astroz_b200.api import Satrec, WGS72
 from tests.golden import tles as G
 sat = Satrec.twoline2rv(*G.ISS, WGS72)
-for n in (1440, 1_209_600, 31_536_000 // 4):
+for n in (1440, 1_209_600, 31_536_000 // 4, 31_536_000):   # ... "1 year (second)", benchmarks/zig_sgp4_bench.zig:46-52
     jd = np.full(n, sat.jdsatepoch); fr = sat.jdsatepochF + np.arange(n) / 86400.0
     for _ in range(2): sat.sgp4_array(jd, fr)
     t0 = time.perf_counter(); K = 5
