@@ -92,7 +92,9 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
                          const GravConsts &g, CellOut (&o)[kN]) {
     double ya[kN], inv_am[kN], axnl[kN], aynl[kN], s[kN], c[kN], eps[kN];
     AZ_LANES {
-        ya[k] = rsqrt_nr(am[k]);  // am^-1/2
+        // am^-1/2 to 2^-46: it scales only J2/J3-sized terms (1/am, am^-3/2, 1/pl), and sqrt(am) below comes out of a
+        // Heron correction that squares the error
+        ya[k] = rsqrt_nr1(am[k]);
         inv_am[k] = ya[k] * ya[k];
         // 1 / (am (1 - em^2)); only scales the 1e-3-sized J3 terms, so the 2^-46 reciprocal is ample
         const double temp = inv_am[k] * rcp_fast(fma(-em[k], em[k], 1.0));
@@ -112,20 +114,22 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
     bool spec = true;
     double s2[kN], c2[kN];
     {
-        double d1[kN], s1[kN], c1[kN];
+        double d1[kN], s1[kN], c1[kN], slope[kN];
         AZ_LANES {
             const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
             const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
-            d1[k] = esine * rcp_fast(1.0 - ecose);
+            slope[k] = rcp_fast(1.0 - ecose);
+            d1[k] = esine * slope[k];
             spec &= !abs_gt(d1[k], kHiMicro);
             double sd, cd;
             sincos_micro(d1[k], sd, cd);
             rotate(s[k], c[k], sd, cd, s1[k], c1[k]);
         }
         AZ_LANES {
+            // second step with the first step's 1 / (1 - e cos E): it moved by e * d1 (< 4e-6 relative here), and it
+            // multiplies a residual below 1e-8 rad
             const double esine = fma(axnl[k], s1[k], -(aynl[k] * c1[k]));
-            const double ecose = fma(axnl[k], c1[k], aynl[k] * s1[k]);
-            const double d = (esine - d1[k]) * rcp_fast(1.0 - ecose);
+            const double d = (esine - d1[k]) * slope[k];
             spec &= abs_lt(d, kHiLinear);
             s2[k] = fma(c1[k], d, s1[k]);
             c2[k] = fma(-s1[k], d, c1[k]);
@@ -196,7 +200,7 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
         const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
         const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
         const double omel2 = 1.0 - fma(axnl[k], axnl[k], aynl[k] * aynl[k]);
-        const double yb = rsqrt_nr(omel2);
+        const double yb = rsqrt_nr1(omel2);  // 2^-46: betal is Heron-corrected, 1/pl scales J2-sized terms only
         const double betal = sqrt_from_rsqrt(omel2, yb);
         const double sqa = sqrt_from_rsqrt(am[k], ya[k]);
         const double rl = am[k] * (1.0 - ecose);
