@@ -114,22 +114,23 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
     bool spec = true;
     double s2[kN], c2[kN];
     {
-        double d1[kN], s1[kN], c1[kN], slope[kN];
+        double d1[kN], s1[kN], c1[kN];
         AZ_LANES {
             const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
             const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
-            slope[k] = rcp_fast(1.0 - ecose);
-            d1[k] = esine * slope[k];
+            d1[k] = esine * rcp_fast(1.0 - ecose);
             spec &= !abs_gt(d1[k], kHiMicro);
             double sd, cd;
             sincos_micro(d1[k], sd, cd);
             rotate(s[k], c[k], sd, cd, s1[k], c1[k]);
         }
         AZ_LANES {
-            // second step with the first step's 1 / (1 - e cos E): it moved by e * d1 (< 4e-6 relative here), and it
-            // multiplies a residual below 1e-8 rad
+            // (reusing the first step's 1 / (1 - e cos E) here would save five instructions, but it moves the result by
+            // e * d1 * d2 ~ 1e-14 rad = 6e-10 km at geostationary radius, outside the reference's own 1e-10 km
+            // layout-equivalence bound, src/Constellation.zig:869, once two launch shapes solve the same cell differently)
             const double esine = fma(axnl[k], s1[k], -(aynl[k] * c1[k]));
-            const double d = (esine - d1[k]) * slope[k];
+            const double ecose = fma(axnl[k], c1[k], aynl[k] * s1[k]);
+            const double d = (esine - d1[k]) * rcp_fast(1.0 - ecose);
             spec &= abs_lt(d, kHiLinear);
             s2[k] = fma(c1[k], d, s1[k]);
             c2[k] = fma(-s1[k], d, c1[k]);
