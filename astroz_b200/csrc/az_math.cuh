@@ -2,7 +2,8 @@
 //
 // Replaces src/simdMath.zig (sincosN :29-97, modTwoPiN :110-122, atan2N :124-177, pow15N :180-182,
 // pow23N :201-212) of the reference.  Design differences, all deliberate:
-//   * sincos: branch-free Cody-Waite (pi/2 in three parts, FMA) + fdlibm minimax kernels, ~1 ulp;
+//   * sincos: branch-free Cody-Waite (pi/2 = 21-bit head + 53-bit tail, FMA) + polynomial kernels fitted for this
+//     pipe (immediate-encodable high-order coefficients, tools/fit_sincos_imm.py), < 2e-16 absolute;
 //     no Payne-Hanek slow path (arguments here are bounded by |x| < ~1e5 rad: years of mean anomaly).
 //   * atan2 is never needed on the SGP4 path: the true-longitude unit vector (sinu, cosu) is already
 //     normalised, so the short-period rotation is applied with an angle-addition (see kernels).
@@ -91,26 +92,23 @@ constexpr double kTwoPi = 6.28318530717958647692528676655900577;
 // slots each time it is materialised -- ncu showed ~230 of 739 instructions per cell were exactly that
 // (profiles/r01_sgp4_grid_notes.md), making the kernel issue-bound instead of fp64-pipe-bound.
 // sin / cos kernels on |r| <= pi/4 (tools/fit_sincos_imm.py): sin r = r + r^3 (s1 + s2 z + ... + s6 z^5),
-// cos r = 1 - z/2 + z^2 (c1 + ... + c6 z^5), z = r^2.  The three highest coefficients of each are fp64 numbers whose low
-// 32 bits are zero -- sm_100 encodes such an operand in the instruction, so the Horner step that uses it reads two
-// register pairs instead of three (a DFMA with three fresh register-pair sources holds the fp64 pipe 3 cycles instead
-// of 2, tools/fp64_probe.cu) -- and the three lowest were re-solved with those fixed: max error 3.5e-16 (sin),
-// 4.2e-17 (cos) in exact arithmetic, the same class as the unconstrained fdlibm minimax set (6e-18 / 5e-19 before the
-// ~1e-16 of rounding both carry).
+// cos r = 1 - z/2 + z^2 (c1 + ... + c5 z^4), z = r^2.  s6, s4 and c5 are fp64 numbers whose low 32 bits are zero --
+// sm_100 encodes such an operand in the instruction, so the Horner step that multiplies by it reads two register pairs
+// instead of three (a DFMA with three fresh register-pair sources holds the fp64 pipe 3 cycles instead of 2,
+// tools/fp64_probe.cu) -- and the other coefficients were re-solved with those fixed.  Max error in exact arithmetic
+// 3.4e-17 (sin), 8.4e-17 (cos): on this interval a sixth cosine coefficient buys nothing, so the cosine kernel is one
+// FMA shorter than fdlibm's, whose unconstrained minimax set reads 6e-18 / 5e-19 before the ~1e-16 of rounding all carry.
 #define AZ_S4 0x1.71de3p-19
-#define AZ_S5 -0x1.ae5dbp-26
 #define AZ_S6 0x1.5d61ep-33
-#define AZ_C4 -0x1.27e4fp-22
-#define AZ_C5 0x1.1ee9ep-29
-#define AZ_C6 -0x1.8faaep-37
+#define AZ_C5 0x1.1bc3fp-29
 // pi/2 = kPio2A (21 significant bits: k * kPio2A is exact for |k| < 2^32) + kPio2B (the next 53 bits); the third part,
 // 1.06e-23, is below 1e-17 for every |x| < 1e6
 #define AZ_PIO2A 0x1.921fbp+0
 #define AZ_PIO2B 0x1.5110b4611a626p-22
 
 struct MathTable {
-    double s1, s2, s3, s4, s5, s6;          // fdlibm __kernel_sin
-    double c1, c2, c3, c4, c5, c6;          // fdlibm __kernel_cos
+    double s1, s2, s3, s4, s5, s6;          // sine kernel
+    double c1, c2, c3, c4, c5, c6;          // cosine kernel (c6 unused: five coefficients)
     double twoOverPi, pio2Hi, pio2Mid, pio2Lo;
     double ts3, ts5, ts7, tc4, tc6, tc8;    // truncated Taylor series for |x| <= 0.05
     double quarterLimit, tinyLimit, clamp, emFloor, keplerTol, invTwoPi, twoPi, pi, microLimit, linearLimit;
@@ -120,10 +118,10 @@ struct MathTable {
 };
 #define AZ_MATH_TABLE_INIT                                                                                    \
     {                                                                                                         \
-        -0x1.55555555550eap-3, 0x1.11111110eaa94p-7, -0x1.a01a018403eabp-13,                                  \
-            AZ_S4, AZ_S5, AZ_S6,                                                                              \
-            0x1.5555555555088p-5, -0x1.6c16c16bccf0cp-10, 0x1.a01a0172105bep-16,                              \
-            AZ_C4, AZ_C5, AZ_C6,                                                                              \
+        -0x1.5555555555480p-3, 0x1.11111111053aep-7, -0x1.a01a019093f40p-13,                                  \
+            AZ_S4, -0x1.ae5c4d5ed16f4p-26, AZ_S6,                                                             \
+            0x1.5555555552f61p-5, -0x1.6c16c167479e5p-10, 0x1.a019fa88a4117p-16,                              \
+            -0x1.27e01d2809545p-22, AZ_C5, 0.0,                                                               \
             6.36619772367581382433e-01, AZ_PIO2A, AZ_PIO2B,                                                  \
             -1.49738490485916983692e-33, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 24.0, -1.0 / 720.0,    \
             1.0 / 40320.0, 0.78, 0.05, 0.95, 1.0e-6, 2.0e-15, 1.0 / 6.28318530717958647692528676655900577,    \
@@ -205,9 +203,9 @@ AZ_HD double sqrt_from_rsqrt(double x, double y) {
 AZ_HD double sqrt_(double x) { return sqrt_from_rsqrt(x, rsqrt_nr(x)); }
 
 // ---- sin / cos --------------------------------------------------------------------------------
-// fdlibm __kernel_sin / __kernel_cos coefficients (public domain, Sun Microsystems), |r| <= pi/4.
+// kernels on |r| <= pi/4 in fdlibm's form (sin r = r + r^3 P(z), cos r = 1 - z/2 + z^2 Q(z)); coefficients above
 AZ_HD double ksin(double r, double r2) {
-    double p = fma(r2, AZ_S6, AZK(s5));  // s6, s4 (c6, c4 below) are immediates; s5 / c5 ride in a register as the addend
+    double p = fma(r2, AZ_S6, AZK(s5));  // s6, s4 (c5 below) are immediates; s5 / c4 ride in a register as the addend
     p = fma(p, r2, AZ_S4);
     p = fma(p, r2, AZK(s3));
     p = fma(p, r2, AZK(s2));
@@ -215,8 +213,7 @@ AZ_HD double ksin(double r, double r2) {
     return fma(p, r2 * r, r);
 }
 AZ_HD double kcos(double r2) {
-    double p = fma(r2, AZ_C6, AZK(c5));
-    p = fma(p, r2, AZ_C4);
+    double p = fma(r2, AZ_C5, AZK(c4));
     p = fma(p, r2, AZK(c3));
     p = fma(p, r2, AZK(c2));
     p = fma(p, r2, AZK(c1));

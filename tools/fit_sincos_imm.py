@@ -6,10 +6,11 @@ On sm_100 a DFMA that reads three fresh 64-bit register pairs occupies the fp64 
 register is such an instruction.  An fp64 operand whose low 32 bits are zero is encoded in the instruction as an
 immediate and costs no register read.  This script re-fits the |r| <= pi/4 kernels
     sin r = r + r^3 (s1 + s2 z + ... + s6 z^5),   cos r = 1 - z/2 + z^2 (c1 + c2 z + ... + c6 z^5),   z = r^2
-with the trailing coefficients constrained to 21 significant bits: the coefficients are rounded one at a time from the
-highest order down, and after each rounding the remaining (full-precision) ones are re-solved by weighted least squares
-on Chebyshev nodes, so they absorb most of the perturbation.  Prints the coefficient tables and the maximum error.
-    python tools/fit_sincos_imm.py [n_imm_sin] [n_imm_cos]
+with chosen coefficients constrained to 21 significant bits: they are rounded one at a time from the highest order
+down, and after each rounding the remaining (full-precision) ones are re-solved by weighted least squares on Chebyshev
+nodes, so they absorb most of the perturbation.  Prints the coefficient tables and the maximum error.
+    python tools/fit_sincos_imm.py            (the shipped design)
+    python tools/fit_sincos_imm.py 6 6        (other coefficient counts, immediates at the same Horner positions)
 """
 import struct
 import sys
@@ -38,12 +39,14 @@ def nodes(n):
     return [PIO4 * mp.cos(mp.pi * (2 * k + 1) / (2 * n)) for k in range(n)]
 
 
-def fit(target, n_coef, n_imm, weight):
-    """coefficients c[0..n_coef) of sum c_k z^k ~ target(z), the last n_imm of them immediates"""
+def fit(target, n_coef, imm_idx, weight):
+    """coefficients c[0..n_coef) of sum c_k z^k ~ target(z); those whose index is in imm_idx are immediates.  They are
+    rounded one at a time from the highest order down, the free ones re-solved after each rounding."""
     rs = [r for r in nodes(160) if r > 0]
     zs = [r * r for r in rs]
     fixed = {}
-    for step in range(n_imm + 1):
+    order = sorted(imm_idx, reverse=True)
+    for step in range(len(order) + 1):
         free = [k for k in range(n_coef) if k not in fixed]
         A = mp.matrix(len(zs), len(free))
         b = mp.matrix(len(zs), 1)
@@ -56,10 +59,9 @@ def fit(target, n_coef, n_imm, weight):
         coef = dict(fixed)
         for j, k in enumerate(free):
             coef[k] = sol[j]
-        if step == n_imm:
+        if step == len(order):
             break
-        k = max(free)
-        fixed[k] = imm(coef[k])
+        fixed[order[step]] = imm(coef[order[step]])
     out = [dbl(coef[k]) if k not in fixed else fixed[k] for k in range(n_coef)]
     return out, sorted(fixed)
 
@@ -73,22 +75,28 @@ def max_err(f, g, n=4001):
 
 
 def main():
-    n_is = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-    n_ic = int(sys.argv[2]) if len(sys.argv) > 2 else 4
-    s, s_imm = fit(lambda r: (mp.sin(r) - r) / r ** 3, 6, n_is, lambda r: r ** 3)
-    c, c_imm = fit(lambda r: (mp.cos(r) - 1 + r * r / 2) / r ** 4, 6, n_ic, lambda r: r ** 4)
+    # shipped design: sin with six coefficients, s6 and s4 immediates (they are the multiplier-side constants of Horner
+    # steps 1 and 2; s5 is the addend of step 1 and sits in a register anyway); cos with FIVE coefficients, c5 immediate
+    # -- on |r| <= pi/4 the sixth cosine coefficient buys nothing at this accuracy, so the kernel is one FMA shorter
+    n_s, imm_s = 6, [5, 3]
+    n_c, imm_c = 5, [4]
+    if len(sys.argv) > 2:
+        n_s, n_c = int(sys.argv[1]), int(sys.argv[2])
+        imm_s, imm_c = [n_s - 1, n_s - 3], [n_c - 1]
+    s, s_imm = fit(lambda r: (mp.sin(r) - r) / r ** 3, n_s, imm_s, lambda r: r ** 3)
+    c, c_imm = fit(lambda r: (mp.cos(r) - 1 + r * r / 2) / r ** 4, n_c, imm_c, lambda r: r ** 4)
 
     def psin(r):
         z = r * r
-        p = s[5]
-        for k in (4, 3, 2, 1, 0):
+        p = s[-1]
+        for k in range(n_s - 2, -1, -1):
             p = p * z + s[k]
         return r + r ** 3 * p
 
     def pcos(r):
         z = r * r
-        p = c[5]
-        for k in (4, 3, 2, 1, 0):
+        p = c[-1]
+        for k in range(n_c - 2, -1, -1):
             p = p * z + c[k]
         return 1 - z / 2 + z * z * p
 
