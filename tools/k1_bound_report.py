@@ -124,19 +124,22 @@ for ln in sass.splitlines():
 start = next((i for i, l in enumerate(fn) if "DFMA" in l and re.search(r"e-1[01]\b|e-0[89]\b", l)), None)
 excerpt = fn[start - 4:start + 26] if start else fn[:30]
 lines.append("Round 1's kernel kept every polynomial coefficient in a register (`LDC.64` then `DFMA p, z, p, Rc`): each Horner step of the four "
-             "range-reduced sincos was a three-pair instruction. The re-fitted kernels (`tools/fit_sincos_imm.py`) put the three highest "
-             "coefficients of sin and cos, the head of π/2 and the 1/6 of the 5-op series in the instruction itself. Excerpt of the shipped "
+             "range-reduced sincos was a three-pair instruction. The re-fitted kernels (`tools/fit_sincos_imm.py`) put two of the six sine "
+             "coefficients (s6, s4), the top one of the five cosine coefficients (c5), the head of π/2 and the 1/6 of the 5-op series in the "
+             "instruction itself (an fp64 immediate must have a zero low word; the fit is redone with those coefficients constrained). Excerpt of the shipped "
              "SASS (three epochs per thread interleaved; note the immediates and the `.reuse` on the shared `z`):\n")
 lines.append("```\n" + "\n".join(excerpt) + "\n```\n")
 lines.append("What remains are products of three live per-cell quantities — `fma(s0, cd, c0*sd)` rotations, `fma(axnl, s, -(aynl*c))`, "
              "`fma(rate, t, angle0)` with per-satellite operands — not constants.\n")
 lines.append("## 4. Why not 100 % of the floor\n")
-lines.append("Three resident warps per scheduler (152 registers) × three epochs per thread give ≤ 9 independent chains against a dependent-issue "
+lines.append("Three CTAs of four warps per SM (three resident warps per scheduler at 165 registers) × three epochs per thread give ≤ 9 independent chains against a dependent-issue "
              "latency of 8.1 cycles and a 2–3-cycle issue interval: enough inside the long polynomial blocks (18–20 stall samples per "
              "instruction) but not inside short dependent phases — reciprocal seeds (MUFU then two dependent FMAs), the quadrant selects "
              "between a sincos' polynomials and its consumers, the Newton steps. The launch-shape sweep (`profiles/r02m_k1_shapes.jsonl`: "
              "2 or 3 epochs per thread × 2–4 CTAs/SM × stripes 256–768) is flat within 2 %, i.e. trading chains for warps does not help; "
              "round 2 instead removed control flow from the hot path (speculative two-step Kepler solve and small rotations with cold "
-             "fall-backs), which merged the short blocks and moved the kernel from 0.437 to 0.40 ms.\n")
+             "fall-backs), which merged the short blocks and moved the kernel from 0.437 to 0.40 ms; the shorter sincos kernels and the Kepler hand-off "
+             "(`profiles/r02r_kepler_handoff.jsonl`) brought it to 0.374 ms = 0.79 of this floor's pipe time, 0.806 of the arithmetic peak "
+             "on the algorithmic FLOP count.\n")
 open(out, "w").write("\n".join(lines))
 print("wrote", out)
