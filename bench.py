@@ -265,6 +265,20 @@ class Harness:
             self.dist.barrier()
         self.torch.cuda.synchronize(self.dev)
 
+    def rank0_section_done(self, key: str):
+        """Rank 0 announces the end of a section it ran alone; the other ranks sleep on the rendezvous store until then.
+        (Waiting inside an NCCL barrier instead keeps one host thread per waiting rank spinning in
+        cudaStreamSynchronize: seven busy CPUs of the pool's 16-CPU quota while rank 0 drives eight GPUs.)"""
+        if self.dist is None:
+            return
+        import datetime
+
+        store = self.dist.distributed_c10d._get_default_store()
+        if self.rank == 0:
+            store.set(key, "1")
+        else:
+            store.wait([key], datetime.timedelta(seconds=1800))
+
     def max_over_ranks(self, x: float) -> float:
         if self.dist is None:
             return x
@@ -463,6 +477,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
                 del multi
             except Exception as exc:
                 legs["single_handle_all_gpus"] = {"unavailable": repr(exc)[:300]}
+        h.rank0_section_done("single_handle_leg")
         h.barrier()
 
     # ---- a device-resident consumer: fused propagate + single-target screen through the host API (N = 1) ----------
