@@ -351,16 +351,53 @@ AZ_HD void sgp4_cell(ColFn col, const double (&t)[kN], const GravConsts &g, Cell
     kepler_posvel<kN>(am, em, mm, argpm, nodem, sa, g, o);
 }
 
-// Angle of the unit vector (s, c) = (sin a, cos a), a in (-pi, pi]: the fp32 arctangent (idle FMA/XU pipes) is the
-// seed, exactly representable in fp64; one first-order correction with the fp64 sincos of the seed finishes it:
-// d = sin(a - a0) = s cos a0 - c sin a0, |d| < 1e-6, asin(d) - d < 2e-19.  22 fp64 instructions against ~54 for
-// libdevice's atan2 (and no constants to materialise).  The sign of a zero s survives the conversion, so the branch
-// cut at +-pi falls where atan2 puts it.
+// Angle of the unit vector (s, c) = (sin a, cos a), a in (-pi, pi].  An fp32 arctangent (idle FMA/XU pipes) is snapped
+// to the lattice a0 = k / 128 rad, whose sines and cosines sit in a 13 KB table (L1-resident; az_angle_table.inc,
+// tools/gen_angle_table.py); d = sin(a - a0) = s cos a0 - c sin a0 with |d| <= 2^-8 + 2e-5, and the three-term arcsine
+// finishes it: the x^7 term is below 7e-19.  8 fp64 instructions against ~54 for libdevice's atan2 (round 1's version
+// ran the full range-reducing sincos on the seed: 28).  A common scale error eps of (s, c) moves the result by eps d <
+// 4e-3 eps.  The sign of a zero s survives the conversion, so the branch cut at +-pi falls where atan2 puts it.
+struct AnglePair { double s, c; };
+static __device__ const AnglePair __align__(16) kAngleTabDev[807] = {
+#include "az_angle_table.inc"
+};
+static const AnglePair kAngleTabHost[807] = {  // the same entries for tests/host_emul
+#include "az_angle_table.inc"
+};
+// fp32 arctangent of (s, c) within 2e-5 rad, branch-free: octant reduction by min / max, a five-term odd polynomial
+// (1.2e-5 on [0, 1]), the octant undone with selects.  libdevice's atan2f is accurate to 2 ulp, which the lattice snap
+// below throws away, and brings 6 branches and a division subroutine per call into an otherwise straight-line epilogue.
+AZ_HD float atan2_seed(float s, float c) {
+    const float ay = fabsf(s), ax = fabsf(c);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+#ifdef __CUDA_ARCH__
+    const float t = __fdividef(mn, mx);
+#else
+    const float t = mn / mx;
+#endif
+    const float t2 = t * t;
+    float p = fmaf(t2, 0.020812865f, -0.085092984f);
+    p = fmaf(p, t2, 0.18011868f);
+    p = fmaf(p, t2, -0.33029541f);
+    p = fmaf(p, t2, 0.99986577f);
+    float r = p * t;
+    r = (ay > ax) ? 1.57079637f - r : r;
+    r = (c < 0.0f) ? 3.14159274f - r : r;
+    return copysignf(r, s);
+}
+
 AZ_HD double angle_of_unit(double s, double c) {
-    const double a0 = (double)atan2f((float)s, (float)c);
-    double s0, c0;
-    sincos_full(a0, s0, c0);
-    return a0 + fma(s, c0, -(c * s0));
+    const float kf = rintf(atan2_seed((float)s, (float)c) * 128.0f);  // |k| <= 402
+    const double a0 = (double)(kf * 0.0078125f);                      // exact
+#ifdef __CUDA_ARCH__
+    const AnglePair t = kAngleTabDev[(int)kf + 403];
+#else
+    const AnglePair t = kAngleTabHost[(int)kf + 403];
+#endif
+    const double d = fma(s, t.c, -(c * t.s));  // |d| <= 2^-8 + 2e-5
+    const double x2 = d * d;
+    const double u = x2 * fma(x2, 0.075, 1.0 / 6.0);  // asin(d) = d (1 + x2 (1/6 + 3/40 x2))
+    return a0 + fma(d, u, d);
 }
 
 // ---- deep space (src/Sdp4Batch.zig:16-125,199-526; src/Sdp4.zig:681-866) --------------------------------
@@ -678,26 +715,22 @@ AZ_HD void ecef_to_geodetic(double &x, double &y, double &z) {
         return;
     }
     // Reciprocal square roots carry one Newton step (2^-46) where that is provably enough: the Heron correction in
-    // sqrt_from_rsqrt squares the error; angle_of_unit is insensitive to a common scale of its arguments (the error is
-    // that scale times its 1e-7-sized residual); the first Bowring evaluation only has to land within the second one's
-    // basin (2e-13 rad), and the height-corrected start needs its 0.7 % term to a few digits.
+    // sqrt_from_rsqrt squares the error; angle_of_unit sees a common scale error of its arguments 4e-3 times smaller;
+    // the height-corrected start needs its 0.7 % term to a few digits.
     const double ip = rsqrt_nr1(p2);
     const double p = sqrt_from_rsqrt(p2, ip);
     const double lon = angle_of_unit(y * ip, x * ip);
+    // Bowring's step from the height-corrected parametric latitude, once: within 2.2e-13 rad (1.4 micrometres on the
+    // ground) of the converged latitude for every height from 100 km to 50,000 km (a second step reaches 3e-16 for
+    // 17 more instructions; the reference's own loop stops when a step moves the latitude by less than 1e-12,
+    // src/WorldCoordinateSystem.zig:107-113)
     const double ir = rsqrt_seed(fma(z, z, p2));
     double su = b * z * fma(ep2b, ir, 1.0), cu = a * p;
-    double num = 0.0, den = 1.0;
-#pragma unroll
-    for (int it = 0; it < 2; ++it) {
-        const double q = fma(su, su, cu * cu);
-        const double h = (it == 0) ? rsqrt_nr1(q) : rsqrt_nr(q);
-        su *= h;
-        cu *= h;
-        num = fma(ep2b * su * su, su, z);
-        den = fma(-e2a * cu * cu, cu, p);
-        su = (1.0 - f) * num;
-        cu = den;
-    }
+    const double hq = rsqrt_nr1(fma(su, su, cu * cu));
+    su *= hq;
+    cu *= hq;
+    const double num = fma(ep2b * su * su, su, z);
+    const double den = fma(-e2a * cu * cu, cu, p);
     const double h = rsqrt_nr1(fma(num, num, den * den));
     const double sl = num * h, cl = den * h;
     const double w2 = fma(-e2 * sl, sl, 1.0);

@@ -125,3 +125,22 @@ def test_geodetic_epilogue_branch_cut_and_axis(emul, oracle):
     assert np.max(np.abs(out[~polar, 2] - ref[~polar, 2])) < 1e-7
     b = 6378.137 * (1.0 - 1.0 / 298.257223563)
     assert np.allclose(out[polar, 2], np.abs(cases[polar, 2]) - b, atol=1e-6)
+
+
+def test_angle_table_is_in_sync_and_dense_angles_round_trip(emul):
+    """astroz_b200/csrc/az_angle_table.inc is what tools/gen_angle_table.py writes, and angle_of_unit (through the
+    geodetic epilogue's longitude) returns atan2 to 3e-16 over a dense sweep of the circle, lattice midpoints included."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "tools", "gen_angle_table.py"), "--check"]).returncode == 0
+    k = np.arange(-402, 403)
+    ang = np.concatenate([k / 128.0, (k + 0.5) / 128.0, (k + 0.4999) / 128.0, np.linspace(-np.pi, np.pi, 20001)])
+    ang = ang[(ang > -np.pi) & (ang < np.pi)]
+    ecef = np.stack([7000.0 * np.cos(ang), 7000.0 * np.sin(ang), np.full_like(ang, 123.0)], axis=1).copy()
+    out = np.zeros_like(ecef)
+    dp = C.POINTER(C.c_double)
+    emul.lib.emul_ecef_to_geodetic(ecef.ctypes.data_as(dp), len(ecef), out.ctypes.data_as(dp))
+    assert np.max(np.abs(out[:, 1] - np.arctan2(ecef[:, 1], ecef[:, 0]))) < 4e-16
