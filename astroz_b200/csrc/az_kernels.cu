@@ -458,7 +458,7 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 #define AZ_K1_STRIPE 384
 #endif
 #ifndef AZ_K1_BLOCKS
-#define AZ_K1_BLOCKS 2
+#define AZ_K1_BLOCKS 3
 #endif
 #ifndef AZ_K1_LANES
 #define AZ_K1_LANES 3

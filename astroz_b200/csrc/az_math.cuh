@@ -115,6 +115,7 @@ struct MathTable {
     // deep-space constants (src/Sdp4.zig:15-52): solar / lunar mean motions, twice their eccentricities, the earth's
     // rotation rate per minute, and the two leading binomial coefficients of (1 + x)^(-2/3)
     double zns, znl, zes2, zel2, rptim, bin1, bin2;
+    double stepInv, stepMid;                // 1024 / (2 pi) and the second word of 2 pi / 1024 (sincos_full)
 };
 #define AZ_MATH_TABLE_INIT                                                                                    \
     {                                                                                                         \
@@ -126,7 +127,8 @@ struct MathTable {
             -1.49738490485916983692e-33, -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 24.0, -1.0 / 720.0,    \
             1.0 / 40320.0, 0.78, 0.05, 0.95, 1.0e-6, 2.0e-15, 1.0 / 6.28318530717958647692528676655900577,    \
             6.28318530717958647692528676655900577, 3.14159265358979323846264338327950288, 2.0e-3, 1.0e-8,     \
-            1.19459e-5, 1.5835218e-4, 2.0 * 0.01675, 2.0 * 0.05490, 4.37526908801129966e-3, -2.0 / 3.0, 5.0 / 9.0 \
+            1.19459e-5, 1.5835218e-4, 2.0 * 0.01675, 2.0 * 0.05490, 4.37526908801129966e-3, -2.0 / 3.0, 5.0 / 9.0, \
+            256.0 * 6.36619772367581382433e-01, AZ_PIO2B / 256.0                                            \
     }
 static __constant__ MathTable kMathDev = AZ_MATH_TABLE_INIT;
 static const MathTable kMathHost = AZ_MATH_TABLE_INIT;
@@ -221,7 +223,46 @@ AZ_HD double kcos(double r2) {
     return fma(p, r2, 1.0);
 }
 
-// sin and cos of x, |x| <~ 1e5.  Cody-Waite with pi/2 = hi + mid (FMA keeps k*hi exact enough).
+// sin and cos of x, |x| <~ 1e5.
+#ifndef AZ_SINCOS_TABLE
+#define AZ_SINCOS_TABLE 1
+#endif
+#if AZ_SINCOS_TABLE
+// Reduction to the 1024-point lattice of the circle: x = k h + r, h = 2 pi / 1024, |r| <= h / 2 = 3.07e-3 (Cody-Waite
+// with h = hi + mid, hi 21 bits so k hi is exact).  (sin, cos)(k h) come from a 16 KB table (az_sincos_table.inc,
+// L1-resident, 40-digit values rounded once); on |r| <= 3.07e-3 sin r = r + r^3 (-1/6 + r^2 / 120) and
+// cos r = 1 + r^2 (-1/2 + r^2 / 24) are exact to 5e-21 / 1.2e-18, and the angle addition finishes it: 14 fp64
+// instructions and no quadrant logic, against 18 plus four selects for the pi/2 reduction with the |r| <= pi/4 kernels
+// (which stay, for the arguments that need no reduction).  1/120 and 1/24 are 21-bit immediates: their rounding moves
+// the result by 6e-22 and 9e-19.
+struct SinCosPair { double s, c; };
+static __device__ const SinCosPair __align__(16) kSinCosTabDev[1024] = {
+#include "az_sincos_table.inc"
+};
+static const SinCosPair kSinCosTabHost[1024] = {  // the same entries for tests/host_emul
+#include "az_sincos_table.inc"
+};
+#define AZ_STEP_A 0x1.921fbp-8  // AZ_PIO2A / 256
+AZ_HD void sincos_full(double x, double &s, double &c) {
+    constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick (imm32-encodable)
+    double kf = fma(x, AZK(stepInv), kMagic);
+    const unsigned q = (unsigned)dbl_lo(kf) & 1023u;
+    kf -= kMagic;
+    double r = fma(-kf, AZ_STEP_A, x);  // exact product (21-bit constant), one rounding
+    r = fma(-kf, AZK(stepMid), r);
+#ifdef __CUDA_ARCH__
+    const SinCosPair t = kSinCosTabDev[q];
+#else
+    const SinCosPair t = kSinCosTabHost[q];
+#endif
+    const double r2 = r * r;
+    const double sr = fma(r * r2, fma(r2, 0x1.11111p-7, AZK(ts3)), r);
+    const double cr = fma(r2, fma(r2, 0x1.55555p-5, -0.5), 1.0);
+    s = fma(t.s, cr, t.c * sr);
+    c = fma(t.c, cr, -(t.s * sr));
+}
+#else
+// Cody-Waite with pi/2 = hi + mid (FMA keeps k*hi exact enough).
 AZ_HD void sincos_full(double x, double &s, double &c) {
     constexpr double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer trick (imm32-encodable)
     double kf = fma(x, AZK(twoOverPi), kMagic);
@@ -238,6 +279,7 @@ AZ_HD void sincos_full(double x, double &s, double &c) {
     s = dbl_xor_hi(a, (q & 2u) << 30);
     c = dbl_xor_hi(b, ((q + 1u) & 2u) << 30);
 }
+#endif
 
 // |x| <= pi/4: the kernels alone, no range reduction.  Used for the Kepler offset E-u (|.| <= e).
 AZ_HD void sincos_quarter(double x, double &s, double &c) {
