@@ -451,9 +451,13 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 }
 
 // Shipped launch shapes (warps per CTA, epochs per stripe, resident CTAs per SM, epochs per thread), from the
-// on-device sweeps in profiles/: the plain satellite-major TEME/ECEF grid likes three epochs per thread (more
-// independent fp64 chains per warp, 158 registers, 2 CTAs/SM: -2.2 %); the time-major transpose and the geodetic
-// epilogue need the registers themselves and are faster with two.
+// on-device sweeps in profiles/.  The plain satellite-major TEME/ECEF grid: three epochs per thread (nine independent
+// fp64 chains per scheduler), 3 resident CTAs / SM (164 registers).  History on the headline grid: two epochs per thread
+// (4, 256, 3, 2) 0.476 ms -> three epochs -2.2 % -> with the table-reduced sincos (az_math.cuh: 14 instead of 18 fp64
+// instructions, no quadrant selects) 0.347 ms at 3 CTAs / SM; the same code at 2 CTAs / SM (184 registers) 0.392 ms,
+// two epochs x 4 CTAs 0.355 ms, stripes of 256 0.389 ms, of 768 0.347 ms (profiles/r02w_sincos_table.jsonl,
+// r02x_k1_shapes.jsonl).  The time-major transpose and the geodetic epilogue need the registers themselves and are
+// faster with two epochs per thread.
 #ifndef AZ_K1_STRIPE
 #define AZ_K1_STRIPE 384
 #endif
