@@ -483,6 +483,14 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 #else
 #define AZ_TIME_MAJOR_K1 AZ_COMPACT_K1
 #endif
+#ifndef AZ_TM_ECEF_LANES
+#define AZ_TM_ECEF_LANES 3   // with the table-reduced sincos the registers are there: 0.489 -> 0.451 ms (profiles/r02y_layout_modes.jsonl)
+#endif
+#if AZ_TM_ECEF_LANES == 3
+#define AZ_TM_ECEF_K1 4, 384, 3, 3
+#else
+#define AZ_TM_ECEF_K1 AZ_COMPACT_K1
+#endif
 #if AZ_GEO_LANES == 3
 #define AZ_GEODETIC_K1 AZ_DEFAULT_K1
 #else
@@ -493,12 +501,14 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 // stages, so a cell is computed by the same instruction stream -- and to the same bits -- whichever way it leaves the SM.
 template <int kLayout, int kMode, bool kVel, int kGather>
 static cudaError_t launch_k1_shaped(const GridArgs &a, cudaStream_t stream) {
-    if constexpr (kMode == 2) {
+    if constexpr (kMode == 2 && kLayout == 1) {  // geodetic: two epochs per thread satellite-major, three time-major
+        return launch_k1<kLayout, kMode, kVel, AZ_TM_ECEF_K1, kGather>(a, stream);
+    } else if constexpr (kMode == 2) {
         return launch_k1<kLayout, kMode, kVel, AZ_GEODETIC_K1, kGather>(a, stream);
     } else if constexpr (kLayout == 1 && kMode == 0) {
         return launch_k1<kLayout, kMode, kVel, AZ_TIME_MAJOR_K1, kGather>(a, stream);
     } else if constexpr (kLayout == 1) {
-        return launch_k1<kLayout, kMode, kVel, AZ_COMPACT_K1, kGather>(a, stream);
+        return launch_k1<kLayout, kMode, kVel, AZ_TM_ECEF_K1, kGather>(a, stream);
     } else {
         // a thread's epochs are 32 apart: short or ragged time axes pad up to 32 * lanes, so take the widest shape
         // that does not add padded warp-runs (16 epochs x 10^6 Monte-Carlo draws: one lane, not three)
