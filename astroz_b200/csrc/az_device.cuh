@@ -86,6 +86,9 @@ AZ_HD void rotate_small_n(const double (&s0)[kN], const double (&c0)[kN], const 
     }
 }
 
+#ifndef AZ_KEP_SERIES
+#define AZ_KEP_SERIES 1
+#endif
 template <int kN>
 AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const double (&mm)[kN],
                          const double (&argpm)[kN], const double (&nodem)[kN], const SatAngles (&sa)[kN],
@@ -120,7 +123,14 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
         AZ_LANES {
             const double esine = fma(axnl[k], s[k], -(aynl[k] * c[k]));
             const double ecose = fma(axnl[k], c[k], aynl[k] * s[k]);
+#if AZ_KEP_SERIES
+            // 1 / (1 - x) = 1 + x + x^2 to x^3 <= 8e-9 for |x| = |e cos E| <= 2e-3 (checked): d1 is off by 1.6e-11 rad at
+            // most, which the second step -- an exact Newton step from wherever the first one landed -- takes out
+            d1[k] = esine * fma(ecose, ecose + 1.0, 1.0);
+            spec &= !abs_gt(ecose, kHiMicro);
+#else
             d1[k] = esine * rcp_fast(1.0 - ecose);
+#endif
             spec &= !abs_gt(d1[k], kHiMicro);
             double sd, cd;
             sincos_micro(d1[k], sd, cd);
@@ -132,7 +142,11 @@ AZ_HD void kepler_posvel(const double (&am)[kN], const double (&em)[kN], const d
             // layout-equivalence bound, src/Constellation.zig:869, once two launch shapes solve the same cell differently)
             const double esine = fma(axnl[k], s1[k], -(aynl[k] * c1[k]));
             const double ecose = fma(axnl[k], c1[k], aynl[k] * s1[k]);
+#if AZ_KEP_SERIES
+            const double d = (esine - d1[k]) * fma(ecose, ecose + 1.0, 1.0);  // |d| < 1e-8: the 8e-9 of the series is 8e-17 rad
+#else
             const double d = (esine - d1[k]) * rcp_fast(1.0 - ecose);
+#endif
             spec &= abs_lt(d, kHiLinear);
             s2[k] = fma(c1[k], d, s1[k]);
             c2[k] = fma(-s1[k], d, c1[k]);
