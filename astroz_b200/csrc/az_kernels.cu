@@ -169,6 +169,13 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks) sgp4_grid_kernel(cons
         mbar_init(&bar, 1);
     }
     __syncthreads();
+    // Programmatic dependent launch (launch_k1 sets the attribute for back-to-back grids of a stream): this CTA may have
+    // been scheduled while the previous kernel's last wave was still draining.  Nothing of global memory is touched
+    // before the wait -- it returns once that kernel has completed and its writes are visible, i.e. ordinary stream
+    // order -- and the next grid in the stream is then allowed to start filling the slots this grid's tail leaves free.
+    // (Both are no-ops for a launch without the attribute.)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;");
     if (threadIdx.x == 0) {
         mbar_expect_tx(&bar, kSgp4TileBytes);
         tma_bulk_g2s(tile, a.sgp4Tiles + (size_t)tileIdx * kSgp4TileDoubles, kSgp4TileBytes, &bar);
@@ -422,6 +429,14 @@ static int k1_resident_slots() {
     }
     return cached[dev];
 }
+// ASTROZ_PDL=0 turns the programmatic dependent launch of back-to-back K1 grids off (measurement / bisecting)
+static bool k1_pdl_enabled() {
+    static const bool on = [] {
+        const char *e = std::getenv("ASTROZ_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
 static uint32_t g_k1StripeOverride = 0;  // measurement only (ASTROZ_K1_STRIPE): epochs per CTA, 0 = automatic
 void set_sgp4_stripe(uint32_t epochs) { g_k1StripeOverride = epochs; }
 
@@ -445,6 +460,22 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
     if (g_k1StripeOverride) stripe = std::max(kPass, g_k1StripeOverride / kPass * kPass);
     a.stripe = stripe;
     dim3 grid(tiles, (a.nTimes + stripe - 1) / stripe);
+    if (kGather == 0 && k1_pdl_enabled()) {
+        // back-to-back grids of one stream (a chunked host call, a caller's time loop): let the next grid's CTAs be
+        // scheduled into the slots this grid's last wave leaves free; the kernel waits for its predecessor before it
+        // touches global memory (griddepcontrol.wait at its top), so stream order is what the data sees
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = dim3(kWarps * 32);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks, kLanes, kGather>, a);
+    }
     sgp4_grid_kernel<kLayout, kMode, kVel, kWarps, kStripe, kMinBlocks, kLanes, kGather>
         <<<grid, kWarps * 32, 0, stream>>>(a);
     return cudaGetLastError();

@@ -21,7 +21,7 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev)
 torch.cuda.set_stream(stream)
 nt = len(jd)
-for stripe in ("0", "384", "192", "96"):
+for stripe in os.environ.get("AZ_STRIPES", "0,384,192,96").split(","):
     os.environ["ASTROZ_K1_STRIPE"] = stripe
     base = None
     for world in (1, 2, 4, 8):
