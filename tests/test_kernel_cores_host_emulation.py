@@ -49,15 +49,31 @@ def emul():
 
 
 def test_sincos_kernel_accuracy(emul):
-    x = np.concatenate([np.linspace(-20.0, 20.0, 4001), np.array([1e3, -5e4, 7.0e5, 1e-300, 0.0])])
+    """sincos_full (az_math.cuh): reduction to the 1024-point lattice of the circle, table entry, two-term remainder
+    series, angle addition.  Dense sweep, lattice edges (the remainder at its maximum), large arguments; against numpy
+    everywhere and against 40-digit values on a subset.  The reference's own bound is 1e-12 (src/simdMath.zig:214-232)."""
+    rng = np.random.default_rng(5)
+    h = 2.0 * np.pi / 1024.0
+    k = np.arange(-1100, 1100)
+    x = np.concatenate([np.linspace(-20.0, 20.0, 4001), (k + 0.5) * h, (k + 0.49999) * h, (k - 0.49999) * h, k * h,
+                        rng.uniform(-1.0e3, 1.0e3, 3000), rng.uniform(-1.0e5, 1.0e5, 3000),
+                        np.array([1e3, -5e4, 7.0e5, 1e-300, 0.0, -0.0, 1e-9])])
     s = np.zeros_like(x)
     c = np.zeros_like(x)
     dp = C.POINTER(C.c_double)
     emul.lib.emul_sincos(x.ctypes.data_as(dp), len(x), s.ctypes.data_as(dp), c.ctypes.data_as(dp))
-    # the kernels carry immediate-encodable coefficients (tools/fit_sincos_imm.py: 3.4e-17 / 8.4e-17 in exact arithmetic)
-    # plus the usual rounding.  The reference's own bound is 1e-12 (src/simdMath.zig:214-232)
     assert np.max(np.abs(s - np.sin(x))) < 4e-16
     assert np.max(np.abs(c - np.cos(x))) < 4e-16
+    assert np.max(np.abs(s * s + c * c - 1.0)) < 6e-16
+    try:
+        import mpmath
+    except ImportError:
+        return
+    mpmath.mp.dps = 40
+    sub = rng.choice(len(x), 1500, replace=False)
+    es = max(abs(mpmath.sin(mpmath.mpf(float(x[i]))) - mpmath.mpf(float(s[i]))) for i in sub)
+    ec = max(abs(mpmath.cos(mpmath.mpf(float(x[i]))) - mpmath.mpf(float(c[i]))) for i in sub)
+    assert es < 3e-16 and ec < 3e-16
 
 
 def test_cores_match_oracle_all_classes(emul, oracle):
