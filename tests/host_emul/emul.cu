@@ -1,6 +1,7 @@
 // TEST INFRASTRUCTURE ONLY: runs the product's __host__ __device__ per-cell cores (az_device.cuh) on the
 // CPU with the product's own host tables, so the kernel arithmetic can be checked against the oracle in
 // a container without a GPU.  Not part of the shipped library; nothing in astroz_b200/ references it.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -30,6 +31,27 @@ extern "C" int emul_constellation_propagate(const char *const *l1, const char *c
         auto col = [&](int i) { return tile[i * kTileSats + sl]; };
         const double toff = (cat.referenceEpochJd - cat.sgp4Epoch[s]) * 1440.0;
         const uint32_t orig = cat.sgp4Orig[s];
+        if (g_lanes == 3) {
+            // the shipped near-earth shape: runs of 96 epochs, a thread owning epochs tw + lane, + 32, + 64 (clamped at
+            // the end of the axis), so the speculative-path flags are ANDed over exactly the cells the kernel groups
+            for (uint32_t tw = 0; tw < nt; tw += 96) {
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    double ts[3];
+                    for (int k = 0; k < 3; ++k) ts[k] = tbase[std::min(tw + 32u * k + lane, nt - 1)] + toff;
+                    CellOut o3[3];
+                    sgp4_cell<3>(col, ts, g, o3);
+                    for (int k = 0; k < 3; ++k) {
+                        const uint32_t tk = tw + 32u * k + lane;
+                        if (tk >= nt) continue;
+                        double *p = pos + ((size_t)orig * nt + tk) * 3, *v = vel + ((size_t)orig * nt + tk) * 3;
+                        p[0] = o3[k].rx; p[1] = o3[k].ry; p[2] = o3[k].rz;
+                        v[0] = o3[k].vx; v[1] = o3[k].vy; v[2] = o3[k].vz;
+                        if (status) status[(size_t)orig * nt + tk] = o3[k].mrt < 1.0 ? 1 : 0;
+                    }
+                }
+            }
+            continue;
+        }
         for (uint32_t t = 0; t < nt; t += g_lanes) {
             CellOut oo[2];
             if (g_lanes == 2) {  // the kernel's 2-epochs-per-thread path (second lane clamped at the end)
@@ -50,10 +72,11 @@ extern "C" int emul_constellation_propagate(const char *const *l1, const char *c
             }
         }
     }
+    const int dsLanes = g_lanes == 2 ? 2 : 1;  // the deep-space grid ships one epoch per thread
     for (uint32_t s = 0; s < cat.nSdp4; ++s) {
         const Sdp4Sat &e = cat.sdp4[s];
         const uint32_t orig = cat.sdp4Orig[s];
-        for (uint32_t t = 0; t < nt; t += g_lanes) {
+        for (uint32_t t = 0; t < nt; t += dsLanes) {
             double ts[2], xli[2], xni[2], atime[2];
             for (int k = 0; k < 2; ++k) {  // the kernel's lattice walk, from node 0 (no lattice cache on the host)
                 const uint32_t tk = t + k < nt ? t + k : nt - 1;
@@ -67,12 +90,12 @@ extern "C" int emul_constellation_propagate(const char *const *l1, const char *c
             }
             CellOut oo[2];
             int st[2] = {0, 0};
-            if (g_lanes == 2) {  // the kernel's 2-epochs-per-thread path
+            if (dsLanes == 2) {  // the two-epochs-per-thread form of the core
                 sdp4_cell_n<2>(e, ts, xli, xni, atime, g, oo, st);
             } else {
                 st[0] = sdp4_cell(e, ts[0], xli[0], xni[0], atime[0], g, oo[0]);
             }
-            for (int k = 0; k < g_lanes && t + k < nt; ++k) {
+            for (int k = 0; k < dsLanes && t + k < nt; ++k) {
                 const CellOut &o = oo[k];
                 double *p = pos + ((size_t)orig * nt + t + k) * 3, *v = vel + ((size_t)orig * nt + t + k) * 3;
                 if (st[k] != 0) { p[0] = p[1] = p[2] = v[0] = v[1] = v[2] = 0.0; }
