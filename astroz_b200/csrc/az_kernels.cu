@@ -487,8 +487,8 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 // (4, 256, 3, 2) 0.476 ms -> three epochs -2.2 % -> with the table-reduced sincos (az_math.cuh: 14 instead of 18 fp64
 // instructions, no quadrant selects) 0.347 ms at 3 CTAs / SM; the same code at 2 CTAs / SM (184 registers) 0.392 ms,
 // two epochs x 4 CTAs 0.355 ms, stripes of 256 0.389 ms, of 768 0.347 ms (profiles/r02w_sincos_table.jsonl,
-// r02x_k1_shapes.jsonl).  The time-major transpose and the geodetic epilogue need the registers themselves and are
-// faster with two epochs per thread.
+// r02x_k1_shapes.jsonl).  The time-major grids take the same three epochs per thread; only the satellite-major geodetic
+// grid, whose epilogue needs the registers itself, is faster with two (profiles/r02y_layout_modes.jsonl, r02z3 for TEME).
 #ifndef AZ_K1_STRIPE
 #define AZ_K1_STRIPE 384
 #endif
@@ -502,9 +502,9 @@ static cudaError_t launch_k1(const GridArgs &a0, cudaStream_t stream) {
 #define AZ_DEFAULT_K1 4, AZ_K1_STRIPE, AZ_K1_BLOCKS, AZ_K1_LANES
 #endif
 #define AZ_COMPACT_K1 4, 256, 3, 2
-// epochs per thread of the time-major and geodetic specialisations (2: the compact shape, 3: the default one)
+// epochs per thread of the time-major and geodetic specialisations (2: the compact shape, 3: stripe 384 x 3 CTAs / SM)
 #ifndef AZ_TM_LANES
-#define AZ_TM_LANES 3   // TEME time-major only: measured 40.4 -> 42.9 G props/s; the ECEF rotation wants the registers back
+#define AZ_TM_LANES 3   // TEME time-major: 0.422 ms against 0.459 ms with two epochs per thread (final build)
 #endif
 #ifndef AZ_GEO_LANES
 #define AZ_GEO_LANES 2
